@@ -1,0 +1,184 @@
+/* storygen_b200 — C ABI of the B200 (sm_100a) kernels behind StoryGen's denoising hot path.
+ *
+ * The reference (haoningwu3639/StoryGen) ships no native code and no FFI: its hot path is a chain of
+ * torch.nn / diffusers / xformers library calls.  Each entry point below replaces one group of those
+ * calls; the comment on each names the reference call sites (file:line in /root/reference) it stands
+ * in for.  INTEGRATION.md shows the ctypes binding used by storygen_b200/ (the Python mirror of the
+ * reference's UNet2DConditionModel / StableDiffusionPipeline).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless stated otherwise; the caller owns every buffer
+ *     (inputs, outputs, workspaces).  The library never allocates or frees device memory and keeps
+ *     no mutable global state besides the lazily resolved driver entry point for tensor-map encoding.
+ *   - Activations are bf16, channel-last: images are (n, y, x, c) = "NHWC", token streams are
+ *     (n, token, c).  Statistics / biases / time embeddings are fp32.
+ *   - Every launcher enqueues on `stream` (a cudaStream_t passed as void*), never synchronises, and
+ *     is CUDA-graph capturable.
+ *   - Return value: 0 on success; negative = invalid argument (SG_ERR_*); positive = cudaError_t of
+ *     a failed launch/encode.  Nothing throws or aborts.
+ */
+#ifndef STORYGEN_B200_H
+#define STORYGEN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_ABI_VERSION 3
+
+#define SG_ERR_SHAPE (-1)   /* unsupported / inconsistent shape            */
+#define SG_ERR_ALIGN (-2)   /* pointer or stride not 16-byte aligned        */
+#define SG_ERR_DRIVER (-3)  /* cuTensorMapEncodeTiled entry point not found */
+#define SG_ERR_ARG (-4)     /* null pointer / bad enum                      */
+
+/* ---- introspection ------------------------------------------------------------------------- */
+int sg_abi_version(void);
+/* sizeof() of the argument structs as compiled, so a binding can verify its mirror. */
+int sg_sizeof_gemm_args(void);
+int sg_sizeof_attn_args(void);
+/* number of kernels this library has launched since load (host counter; bench "gpu_launches") */
+int64_t sg_launch_count(void);
+const char* sg_error_string(int code);
+
+/* ---- tcgen05 GEMM / implicit-GEMM convolution ------------------------------------------------
+ * out[m, :] = epilogue( sum_k A[m, k] * B[:, k] ),  A assembled on the fly from up to 4 NHWC source
+ * tensors by TMA: the K loop walks `segs`; segment s contributes nkb*64 consecutive channels
+ * [c0, c0 + 64*nkb) of source `src`, read at pixel (x + dx, y + dy) of the output pixel (x, y)
+ * (out-of-image reads return 0 = zero padding).  A plain Linear is one segment with dx = dy = 0 over
+ * a (1, 1, M, K) "image"; a 3x3 conv is 9 segments; conv + 1x1 shortcut + channel concat are just
+ * more segments.  B is the pre-packed weight [N, Ktot] (bf16, K contiguous, K ordered as `segs`).
+ *
+ * Replaces: nn.Conv2d 3x3 / 1x1 and nn.Linear calls of ResnetBlock2D, Downsample2D, Upsample2D
+ * (model/unet_2d_blocks.py:222-233,332-368,552-584), Transformer2DModel.proj_in/proj_out
+ * (model/attention.py:59,83,100,118), CrossAttention.to_q/to_k/to_v/to_out (model/attention.py:
+ * 175-223 via diffusers), FeedForward/GEGLU (model/attention.py:347-350,391-393), the skip
+ * torch.cat (model/unet_2d_blocks.py:609,626,716) and the residual adds (model/attention.py:262,
+ * 277,291-293,300; ResnetBlock2D output).
+ */
+typedef struct sg_src {
+  const void* ptr;                    /* bf16, 16-byte aligned                              */
+  int64_t dim_c, dim_w, dim_h, dim_n; /* extents (elements)                                 */
+  int64_t stride_w, stride_h, stride_n; /* element strides (channel stride is 1); *2 % 16 == 0 */
+} sg_src;
+
+typedef struct sg_seg {
+  int32_t src; /* index into sg_gemm_args.src */
+  int32_t dx, dy;
+  int32_t c0;  /* first channel                */
+  int32_t nkb; /* number of 64-channel blocks  */
+} sg_seg;
+
+#define SG_MAX_SRC 4
+#define SG_MAX_SEGS 24
+
+#define SG_EPI_LINEAR 0 /* out = acc + bias + lane_bias + res_scale * residual            */
+#define SG_EPI_GEGLU 1  /* B rows interleaved [16 value | 16 gate]; out = v * gelu_erf(g) */
+
+typedef struct sg_gemm_args {
+  int32_t num_src;
+  int32_t num_segs;
+  sg_src src[SG_MAX_SRC];
+  sg_seg segs[SG_MAX_SEGS];
+  /* output pixel grid and the 128-row tile box (bw * bh * bn == 128) */
+  int32_t out_w, out_h, out_n;
+  int32_t bw, bh, bn;
+  /* weights */
+  const void* b; /* bf16 [N, Ktot] */
+  int64_t N, Ktot;
+  /* epilogue */
+  int32_t mode;
+  float res_scale;
+  const float* bias;      /* [N] (pre-activation columns) or NULL */
+  const float* lane_bias; /* [out_n, N] or NULL (per-image row bias: time embedding)      */
+  const void* residual;   /* bf16 [M, ldr] or NULL (M = out_n*out_h*out_w rows)           */
+  int64_t ldr;
+  void* out; /* bf16 [M, ldo] */
+  int64_t ldo;
+} sg_gemm_args;
+
+int sg_gemm(const sg_gemm_args* args, void* stream);
+
+/* ---- fused attention core (FlashAttention-style, tcgen05 + TMEM) -----------------------------
+ * o[n, q, h*d:(h+1)*d] = softmax(scale * Q_h K_h^T) V_h for every (n, h); Q/K/V are read in place
+ * from (n, token, channel) bf16 tensors with arbitrary row strides (so a fused QKV projection
+ * output can be consumed directly).  Image lane n reads K/V lane kv_lane_div ? n / kv_lane_div : n.
+ *
+ * Replaces: CrossAttention core of attn1 / attn2 / attn3 — baddbmm + softmax + bmm or
+ * xformers.ops.memory_efficient_attention (model/attention.py:255-260, 271-276, 285-290 via
+ * diffusers CrossAttention; enabled at inference.py:58-64).
+ */
+typedef struct sg_attn_args {
+  const void* q; /* element (n, i, c) at q + n*q_stride_n + i*q_stride_t + c */
+  const void* k;
+  const void* v;
+  void* o;
+  int64_t q_stride_n, q_stride_t;
+  int64_t k_stride_n, k_stride_t;
+  int64_t v_stride_n, v_stride_t;
+  int64_t o_stride_n, o_stride_t;
+  int32_t n_lanes, n_heads, head_dim; /* head_dim in {40, 80, 160} (any multiple of 8 <= 192) */
+  int32_t nq, nk;
+  int32_t n_kv_lanes; /* K/V lanes; lane n uses K/V lane n % n_kv_lanes... see kv_map */
+  const int32_t* kv_map; /* optional device int32[n_lanes]: K/V lane of each Q lane; NULL = identity */
+  float scale;        /* softmax scale (head_dim^-0.5)                                        */
+} sg_attn_args;
+
+int sg_attention(const sg_attn_args* args, void* stream);
+
+/* ---- normalisation / elementwise kernels (HBM-bound) ---------------------------------------- */
+
+/* GroupNorm statistics over an NHWC tensor that is the channel-concat of up to two sources.
+ * stats[n, g] = (mean, rstd) fp32.  Replaces the reduction half of nn.GroupNorm
+ * (ResnetBlock2D.norm1/norm2, Transformer2DModel.norm model/attention.py:55,98, conv_norm_out
+ * model/unet_2d_condition.py:259-262,477-479). */
+int sg_groupnorm_stats(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img,
+                       int32_t hw, int32_t groups, float eps, float* stats, void* stream);
+/* y = (x - mean) * rstd * gamma + beta, optionally followed by SiLU; x = concat(x0, x1) along c. */
+int sg_groupnorm_apply(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img,
+                       int32_t hw, int32_t groups, const float* stats, const float* gamma,
+                       const float* beta, int32_t silu, void* y, void* stream);
+
+/* LayerNorm over the channel dim of a (rows, c) bf16 tensor; up to two affine outputs from one
+ * statistics pass (norm2 and norm4 read the same tensor, model/attention.py:268,283). */
+int sg_layernorm(const void* x, int64_t rows, int32_t c, float eps, const float* gamma_a,
+                 const float* beta_a, void* y_a, const float* gamma_b, const float* beta_b,
+                 void* y_b, void* stream);
+
+/* Sinusoidal timestep features [cos | sin] (flip_sin_to_cos=True, freq_shift=0), fp32 -> bf16.
+ * Replaces diffusers Timesteps (model/unet_2d_condition.py:392). */
+int sg_timestep_features(const float* t, int32_t n, int32_t dim, void* out_bf16, void* stream);
+
+/* Small dense layers on (n, k) rows where n is the image-lane count (time embedding MLP and the 22
+ * time_emb_proj layers): out = act_out(W * act_in(x) + b); x, out fp32; W bf16 [m, k].
+ * Replaces TimestepEmbedding and ResnetBlock2D.time_emb_proj (model/unet_2d_condition.py:398). */
+int sg_small_linear(const float* x, int32_t n, int32_t k, const void* w, const float* b, int32_t m,
+                    int32_t silu_in, int32_t silu_out, float* out, void* stream);
+
+/* Nearest-neighbour 2x upsample NHWC bf16 (Upsample2D, model/unet_2d_blocks.py:581-584,656-658). */
+int sg_upsample2x(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream);
+
+/* conv_in: 3x3 conv, NCHW fp32 (cin<=8) -> NHWC bf16 (model/unet_2d_condition.py:124,411). */
+int sg_conv_in(const float* x_nchw, int32_t n, int32_t cin, int32_t h, int32_t w, const float* wgt,
+               const float* bias, int32_t cout, void* y_nhwc, void* stream);
+/* conv_out: 3x3 conv NHWC bf16 (already GN+SiLU'd) -> NCHW fp32, cout<=8
+ * (model/unet_2d_condition.py:268,480). */
+int sg_conv_out(const void* x_nhwc, int32_t n, int32_t cin, int32_t h, int32_t w, const float* wgt,
+                const float* bias, int32_t cout, float* y_nchw, void* stream);
+
+/* x_t = sqrt(acp[t]) * x + sqrt(1 - acp[t]) * eps  (DDIMScheduler.add_noise at
+ * model/pipeline.py:420-424); per-image timestep index t[n]; all fp32; numel per image = chw. */
+int sg_add_noise(const float* x, const float* eps, const float* acp, const int32_t* t, int32_t n,
+                 int32_t chw, float* out, void* stream);
+
+/* Dual classifier-free guidance + eta=0 DDIM update (model/pipeline.py:456-461):
+ *   e = u + s_img (i - u) + s_txt (a - i);  x0 = (x - sqrt(1-a_t) e)/sqrt(a_t);
+ *   x' = sqrt(a_prev) x0 + sqrt(1 - a_prev) e.
+ * eps3 = (3, b, chw) lanes [uncond | image | all]; latents updated in place. */
+int sg_cfg_ddim_step(const float* eps3, float* latents, int32_t b, int32_t chw, float s_img,
+                     float s_txt, float alpha_t, float alpha_prev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STORYGEN_B200_H */

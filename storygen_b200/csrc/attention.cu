@@ -1,0 +1,347 @@
+// Fused attention core for sm_100a: o = softmax(scale * Q K^T) V per (image lane, head), one CTA per
+// 128-query tile, S / P / O resident in TMEM, K/V streamed by TMA.
+//
+//   warp 0     : TMA loader   Q tile once; K/V tiles of 128 keys through a ring of smem slots in the
+//                             exact order the tensor core consumes them (K0 K1 V0 K2 V1 ...)
+//   warp 1     : MMA issuer   S[b] = Q K_j^T            (tcgen05.mma SS, M=128 N=128, K = head_dim)
+//                             O   += P_j V_j            (tcgen05.mma TS: P read from TMEM, V MN-major)
+//                             QK^T of tile j+1 is issued before waiting for the softmax of tile j
+//   warps 2..5 : softmax      one thread per query row (= TMEM lane): S row -> registers, running max
+//                             with lazy rescale of the O row (only when the max grew by > 2^8),
+//                             exp2, row sum, P (bf16) written back over S, final O / l -> global.
+//
+// Q/K/V are read in place from (lane, token, channel) tensors; a head's [tokens x d] slice is fetched
+// as ceil(d/64) swizzle-128B atoms of 64 channels starting at channel h*d.  Channels past d inside the
+// last atom belong to the next head (or are TMA zero fill): they are neutralised by zeroing the padded
+// Q chunk in smem (QK^T) and by never storing the corresponding O columns (PV).
+#include "common.cuh"
+
+namespace sg {
+
+constexpr int kAttnThreads = 192;
+constexpr int kAtomBytes = 128 * 128;  // [128 rows x 64 bf16], swizzle 128B
+
+struct AttnKParams {
+  CUtensorMap q_map, k_map, v_map;
+  bf16* o;
+  long long o_stride_n, o_stride_t;
+  const int* kv_map;
+  int nq, nk, n_heads;
+  float scale_log2;  // scale * log2(e)
+};
+
+template <int D>
+struct AttnCfg {
+  static constexpr int NA = (D + 63) / 64;   // 64-channel atoms per tile
+  static constexpr int KQ = (D + 15) / 16;   // k-steps of Q K^T
+  static constexpr int kTileBytes = NA * kAtomBytes;
+  static constexpr int kSlots = (NA == 1) ? 8 : (NA == 2 ? 5 : 3);
+  static constexpr int kSmemBytes = kTileBytes * (1 + kSlots) + 1024 + 256;
+  static constexpr int kColS0 = 0, kColS1 = 128, kColO = 256;
+  static constexpr int kTmemCols = 512;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = AttnCfg<D>;
+  constexpr int NA = Cfg::NA;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* kv_smem = smem + Cfg::kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kTileBytes * (1 + Cfg::kSlots));
+  uint64_t* kv_full = bars;                    // [kSlots]
+  uint64_t* kv_empty = bars + Cfg::kSlots;     // [kSlots]
+  uint64_t* q_full = bars + 2 * Cfg::kSlots;   // TMA -> softmax warps
+  uint64_t* q_ready = q_full + 1;              // softmax warps -> MMA (Q pad zeroed)
+  uint64_t* s_full = q_ready + 1;              // [2] MMA -> softmax
+  uint64_t* p_full = s_full + 2;               // [2] softmax -> MMA
+  uint64_t* o_done = p_full + 2;               // MMA -> softmax (PV_j retired)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int T = (p.nk + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kSlots; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(q_full, 1);
+    mbar_init(q_ready, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+    }
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA loader =====================
+    if (lane == 0) {
+      const int kv_img = (p.kv_map != nullptr) ? p.kv_map[img] : img;
+      mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+        tma_load_3d(q_smem + a * kAtomBytes, &p.q_map, q_full, head * D + 64 * a, q0, img);
+      int slot = 0;
+      uint32_t phase = 0;
+      auto load_tile = [&](const CUtensorMap* map, int key0) {
+        mbar_wait(&kv_empty[slot], phase ^ 1);
+        mbar_arrive_expect_tx(&kv_full[slot], Cfg::kTileBytes);
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          tma_load_3d(kv_smem + slot * Cfg::kTileBytes + a * kAtomBytes, map, &kv_full[slot],
+                      head * D + 64 * a, key0, kv_img);
+        if (++slot == Cfg::kSlots) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      for (int s = 0; s <= T; ++s) {
+        if (s < T) load_tile(&p.k_map, s * 128);
+        if (s >= 1) load_tile(&p.v_map, (s - 1) * 128);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
+      int slot = 0;
+      uint32_t phase = 0;
+      const uint32_t q_addr = smem_u32(q_smem);
+      auto issue_qk = [&](int j) {
+        mbar_wait(&kv_full[slot], phase);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(kv_smem + slot * Cfg::kTileBytes);
+        const uint32_t d_tmem = tmem_base + ((j & 1) ? Cfg::kColS1 : Cfg::kColS0);
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KQ; ++ks) {
+          const uint32_t off = (ks >> 2) * kAtomBytes + (ks & 3) * 32;
+          umma_ss(d_tmem, make_smem_desc(q_addr + off, 16, 1024, kLayoutSW128),
+                  make_smem_desc(k_addr + off, 16, 1024, kLayoutSW128), idesc_qk, ks != 0);
+        }
+        umma_commit(&kv_empty[slot]);
+        umma_commit(&s_full[j & 1]);
+        if (++slot == Cfg::kSlots) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      mbar_wait(q_ready, 0);
+      tc_fence_after();
+      issue_qk(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_qk(j + 1);
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        mbar_wait(&kv_full[slot], phase);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(kv_smem + slot * Cfg::kTileBytes);
+        const uint32_t p_tmem = tmem_base + ((j & 1) ? Cfg::kColS1 : Cfg::kColS0);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            // V tile rows = keys (128 B pitch); 16 keys per k-step = 2048 B
+            umma_ts(tmem_base + Cfg::kColO + 64 * a, p_tmem + ks * 8,
+                    make_smem_desc(v_addr + a * kAtomBytes + ks * 2048, kAtomBytes, 1024, kLayoutSW128),
+                    idesc_pv, (j | ks) != 0);
+          }
+        }
+        umma_commit(&kv_empty[slot]);
+        umma_commit(o_done);
+        if (++slot == Cfg::kSlots) {
+          slot = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+
+    mbar_wait(q_full, 0);
+    if constexpr (D % 16 != 0) {
+      // zero Q channels [D, D+8): 16-byte chunk (D/8 % 8) of atom D/64, XOR-swizzled by row
+      constexpr int atom = D / 64;
+      constexpr int chunk = (D % 64) / 8;
+      uint4* dst = reinterpret_cast<uint4*>(q_smem + atom * kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4));
+      *dst = make_uint4(0, 0, 0, 0);
+      fence_proxy_async_smem();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(q_ready);
+
+    float m_used = 0.f, l_run = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1;
+      mbar_wait(&s_full[b], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_tmem = tmem_base + lane_base + (b ? Cfg::kColS1 : Cfg::kColS0);
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
+      tmem_ld_wait();
+      const int valid = p.nk - j * 128;  // keys valid in this tile (>= 1)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(sv[c][i]);
+          if (valid < 128 && (c * 32 + i) >= valid) s = -INFINITY;
+          sv[c][i] = __float_as_uint(s);
+          mx = fmaxf(mx, s);
+        }
+      const float mt = mx * p.scale_log2;
+      float alpha = 1.f;
+      bool need = false;
+      if (j == 0) {
+        m_used = mt;
+      } else if (mt > m_used + 8.f) {
+        alpha = fast_exp2(m_used - mt);
+        m_used = mt;
+        need = true;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        mbar_wait(o_done, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2 * NA; ++c) {
+          uint32_t ov[32];
+          tmem_ld32(tmem_base + lane_base + Cfg::kColO + c * 32, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+          tmem_st32(tmem_base + lane_base + Cfg::kColO + c * 32, ov);
+        }
+      }
+      float sum = 0.f;
+      uint32_t pk[2][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float e0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_used));
+          float e1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, -m_used));
+          sum += e0 + e1;
+          pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
+        }
+      l_run = l_run * alpha + sum;
+      tmem_st32(s_tmem, pk[0]);
+      tmem_st32(s_tmem + 32, pk[1]);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+    }
+
+    // final: O / l  -> global (only the d valid channels of this head)
+    mbar_wait(o_done, (T - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int q = q0 + r;
+    bf16* orow = p.o + static_cast<long long>(img) * p.o_stride_n + static_cast<long long>(q) * p.o_stride_t +
+                 head * D;
+#pragma unroll
+    for (int c = 0; c < 2 * NA; ++c) {
+      if (c * 32 < D) {
+        uint32_t ov[32];
+        tmem_ld32(tmem_base + lane_base + Cfg::kColO + c * 32, ov);
+        tmem_ld_wait();
+        if (q < p.nq) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (c * 32 + g * 8 < D) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(ov[8 * g + 0]) * inv_l, __uint_as_float(ov[8 * g + 1]) * inv_l);
+              w.y = pack_bf16x2(__uint_as_float(ov[8 * g + 2]) * inv_l, __uint_as_float(ov[8 * g + 3]) * inv_l);
+              w.z = pack_bf16x2(__uint_as_float(ov[8 * g + 4]) * inv_l, __uint_as_float(ov[8 * g + 5]) * inv_l);
+              w.w = pack_bf16x2(__uint_as_float(ov[8 * g + 6]) * inv_l, __uint_as_float(ov[8 * g + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = w;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int D>
+static int launch_attn(const AttnKParams& kp, dim3 grid, cudaStream_t stream) {
+  using Cfg = AttnCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  attn_kernel<D><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(kp);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+static int make_tok_map(CUtensorMap* m, const void* ptr, int channels, int tokens, int lanes, int64_t stride_t,
+                        int64_t stride_n) {
+  uint64_t dims[3] = {static_cast<uint64_t>(channels), static_cast<uint64_t>(tokens),
+                      static_cast<uint64_t>(lanes)};
+  uint64_t strides[2] = {static_cast<uint64_t>(stride_t) * 2, static_cast<uint64_t>(stride_n) * 2};
+  uint32_t box[3] = {64, 128, 1};
+  return encode_tmap_bf16(m, ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" int sg_attention(const sg_attn_args* a, void* stream_v) {
+  if (a == nullptr || !a->q || !a->k || !a->v || !a->o) return SG_ERR_ARG;
+  if (a->nq < 1 || a->nk < 1 || a->n_lanes < 1 || a->n_heads < 1) return SG_ERR_SHAPE;
+  if (a->head_dim != 40 && a->head_dim != 80 && a->head_dim != 160) return SG_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(a->o) & 15) || (a->o_stride_t % 8) || (a->o_stride_n % 8)) return SG_ERR_ALIGN;
+  const int C = a->n_heads * a->head_dim;
+  const int kv_lanes = a->n_kv_lanes > 0 ? a->n_kv_lanes : a->n_lanes;
+  AttnKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  int rc;
+  if ((rc = make_tok_map(&kp.q_map, a->q, C, a->nq, a->n_lanes, a->q_stride_t, a->q_stride_n)) != 0) return rc;
+  if ((rc = make_tok_map(&kp.k_map, a->k, C, a->nk, kv_lanes, a->k_stride_t, a->k_stride_n)) != 0) return rc;
+  if ((rc = make_tok_map(&kp.v_map, a->v, C, a->nk, kv_lanes, a->v_stride_t, a->v_stride_n)) != 0) return rc;
+  kp.o = static_cast<bf16*>(a->o);
+  kp.o_stride_n = a->o_stride_n;
+  kp.o_stride_t = a->o_stride_t;
+  kp.kv_map = a->kv_map;
+  kp.nq = a->nq;
+  kp.nk = a->nk;
+  kp.n_heads = a->n_heads;
+  kp.scale_log2 = a->scale * 1.4426950408889634f;
+  dim3 grid((a->nq + 127) / 128, a->n_heads, a->n_lanes);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  switch (a->head_dim) {
+    case 40: return launch_attn<40>(kp, grid, stream);
+    case 80: return launch_attn<80>(kp, grid, stream);
+    default: return launch_attn<160>(kp, grid, stream);
+  }
+}

@@ -1,0 +1,377 @@
+// Persistent warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   warp 0      : TMA producer  (A tiles gathered from NHWC sources with per-segment pixel shifts,
+//                                B = pre-packed weights), kStages-deep smem ring
+//   warp 1      : MMA issuer    (one elected lane; tcgen05.mma M=128 x N=BN x K=16, fp32 in TMEM,
+//                                two accumulator stages so the epilogue of tile i overlaps tile i+1)
+//   warps 2..5  : epilogue      (tcgen05.ld -> bias / time-embedding / residual / GEGLU -> bf16 stores)
+//
+// Tile = 128 output pixels (a bw x bh x bn box of the NHWC output grid) x BN output channels.
+// K loop = list of segments (source tensor, dx, dy, first channel, #64-channel blocks): this one
+// kernel is Linear, 1x1 conv, 3x3 conv (stride 1 or, via phase-strided sources, stride 2), conv over
+// a channel-concat of two tensors, and conv + fused 1x1 shortcut.  See include/storygen_b200.h.
+#include "common.cuh"
+
+namespace sg {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // one 128-byte swizzle atom of bf16
+constexpr int kGemmThreads = 192;
+
+struct GemmKParams {
+  CUtensorMap a_maps[SG_MAX_SRC];
+  CUtensorMap b_map;
+  sg_seg segs[SG_MAX_SEGS];
+  int num_segs;
+  int total_kb;
+  int out_w, out_h, out_n;
+  int bw, bh, bn;
+  int tiles_x, tiles_y, tiles_n;  // M tiles = tiles_x * tiles_y * tiles_n
+  int num_n_tiles;
+  int N;
+  int mode;
+  float res_scale;
+  const float* bias;
+  const float* lane_bias;
+  const bf16* residual;
+  long long ldr;
+  bf16* out;
+  long long ldo;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    gemm_kernel(const __grid_constant__ GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                      // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;      // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int num_tiles = num_m_tiles * p.num_n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&p.b_map);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.num_n_tiles;
+        const int nt = tile - mt * p.num_n_tiles;
+        const int tx = mt % p.tiles_x;
+        const int ty = (mt / p.tiles_x) % p.tiles_y;
+        const int tn = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+        int kb = 0;
+        for (int s = 0; s < p.num_segs; ++s) {
+          const sg_seg seg = p.segs[s];
+          const CUtensorMap* amap = &p.a_maps[seg.src];
+          for (int j = 0; j < seg.nkb; ++j, ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(smem_a + stage * Cfg::kABytes, amap, &full_bar[stage], seg.c0 + j * kBK,
+                        x0 + seg.dx, y0 + seg.dy, n0);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * kBK,
+                        nt * BN);
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+          const uint64_t a_desc = make_smem_desc(a_addr, 16, 1024, kLayoutSW128);
+          const uint64_t b_desc = make_smem_desc(b_addr, 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (>>4) address field
+            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool geglu = (p.mode == SG_EPI_GEGLU);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.num_n_tiles;
+      const int nt = tile - mt * p.num_n_tiles;
+      const int tx = mt % p.tiles_x;
+      const int ty = (mt / p.tiles_x) % p.tiles_y;
+      const int tn = mt / (p.tiles_x * p.tiles_y);
+      const int x = tx * p.bw + r % p.bw;
+      const int y = ty * p.bh + (r / p.bw) % p.bh;
+      const int n = tn * p.bn + r / (p.bw * p.bh);
+      const bool row_ok = (x < p.out_w) && (y < p.out_h) && (n < p.out_n);
+      const long long m = (static_cast<long long>(n) * p.out_h + y) * p.out_w + x;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_row + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = nt * BN + c * 32;
+        if (col0 < p.N && row_ok) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 b = __ldg(b4 + j);
+              f[4 * j + 0] += b.x;
+              f[4 * j + 1] += b.y;
+              f[4 * j + 2] += b.z;
+              f[4 * j + 3] += b.w;
+            }
+          }
+          if (p.lane_bias != nullptr) {
+            const float4* b4 =
+                reinterpret_cast<const float4*>(p.lane_bias + static_cast<long long>(n) * p.N + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 b = __ldg(b4 + j);
+              f[4 * j + 0] += b.x;
+              f[4 * j + 1] += b.y;
+              f[4 * j + 2] += b.z;
+              f[4 * j + 3] += b.w;
+            }
+          }
+          if (!geglu) {
+            if (p.residual != nullptr) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 q = __ldg(r4 + j);
+                float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), cc = unpack_bf16x2(q.z),
+                       d = unpack_bf16x2(q.w);
+                f[8 * j + 0] += p.res_scale * a.x;
+                f[8 * j + 1] += p.res_scale * a.y;
+                f[8 * j + 2] += p.res_scale * b.x;
+                f[8 * j + 3] += p.res_scale * b.y;
+                f[8 * j + 4] += p.res_scale * cc.x;
+                f[8 * j + 5] += p.res_scale * cc.y;
+                f[8 * j + 6] += p.res_scale * d.x;
+                f[8 * j + 7] += p.res_scale * d.y;
+              }
+            }
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + m * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q;
+              q.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              o4[j] = q;
+            }
+          } else {
+            // columns [0,16) = value, [16,32) = gate (weights pre-interleaved on the host)
+            float g[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = f[j] * gelu_erf(f[16 + j]);
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + m * p.ldo + (col0 >> 1));
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              uint4 q;
+              q.x = pack_bf16x2(g[8 * j + 0], g[8 * j + 1]);
+              q.y = pack_bf16x2(g[8 * j + 2], g[8 * j + 3]);
+              q.z = pack_bf16x2(g[8 * j + 4], g[8 * j + 5]);
+              q.w = pack_bf16x2(g[8 * j + 6], g[8 * j + 7]);
+              o4[j] = q;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+static int launch_gemm(const GemmKParams& kp, int num_tiles, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  gemm_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
+  if (a == nullptr || a->b == nullptr || a->out == nullptr) return SG_ERR_ARG;
+  if (a->num_src < 1 || a->num_src > SG_MAX_SRC || a->num_segs < 1 || a->num_segs > SG_MAX_SEGS)
+    return SG_ERR_ARG;
+  if (a->bw * a->bh * a->bn != kBM || a->bw > 256 || a->bh > 256 || a->bn > 256) return SG_ERR_SHAPE;
+  if (a->N % 32 != 0 || a->Ktot % kBK != 0) return SG_ERR_SHAPE;
+  if (a->mode != SG_EPI_LINEAR && a->mode != SG_EPI_GEGLU) return SG_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(a->out) & 15) || (a->ldo % 8) ||
+      (a->residual && ((reinterpret_cast<uintptr_t>(a->residual) & 15) || (a->ldr % 8))))
+    return SG_ERR_ALIGN;
+
+  GemmKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  int total_kb = 0;
+  for (int s = 0; s < a->num_segs; ++s) {
+    const sg_seg& sgm = a->segs[s];
+    if (sgm.src < 0 || sgm.src >= a->num_src || sgm.nkb < 1 || sgm.c0 % 8 != 0) return SG_ERR_ARG;
+    if (sgm.c0 + sgm.nkb * kBK > a->src[sgm.src].dim_c) return SG_ERR_SHAPE;
+    kp.segs[s] = sgm;
+    total_kb += sgm.nkb;
+  }
+  if (static_cast<int64_t>(total_kb) * kBK != a->Ktot) return SG_ERR_SHAPE;
+
+  for (int i = 0; i < a->num_src; ++i) {
+    const sg_src& s = a->src[i];
+    uint64_t dims[4] = {static_cast<uint64_t>(s.dim_c), static_cast<uint64_t>(s.dim_w),
+                        static_cast<uint64_t>(s.dim_h), static_cast<uint64_t>(s.dim_n)};
+    uint64_t strides[3] = {static_cast<uint64_t>(s.stride_w) * 2, static_cast<uint64_t>(s.stride_h) * 2,
+                           static_cast<uint64_t>(s.stride_n) * 2};
+    uint32_t box[4] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(a->bw),
+                       static_cast<uint32_t>(a->bh), static_cast<uint32_t>(a->bn)};
+    int rc = encode_tmap_bf16(&kp.a_maps[i], s.ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != 0) return rc;
+  }
+
+  const int bn_tile = (a->N % 256 == 0) ? 256 : ((a->N % 160 == 0) ? 160 : ((a->N % 128 == 0) ? 128 : 64));
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(a->Ktot), static_cast<uint64_t>(a->N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(a->Ktot) * 2};
+    uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(bn_tile)};
+    int rc = encode_tmap_bf16(&kp.b_map, a->b, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != 0) return rc;
+  }
+
+  kp.num_segs = a->num_segs;
+  kp.total_kb = total_kb;
+  kp.out_w = a->out_w;
+  kp.out_h = a->out_h;
+  kp.out_n = a->out_n;
+  kp.bw = a->bw;
+  kp.bh = a->bh;
+  kp.bn = a->bn;
+  kp.tiles_x = (a->out_w + a->bw - 1) / a->bw;
+  kp.tiles_y = (a->out_h + a->bh - 1) / a->bh;
+  kp.tiles_n = (a->out_n + a->bn - 1) / a->bn;
+  kp.num_n_tiles = static_cast<int>((a->N + bn_tile - 1) / bn_tile);
+  kp.N = static_cast<int>(a->N);
+  kp.mode = a->mode;
+  kp.res_scale = a->res_scale;
+  kp.bias = a->bias;
+  kp.lane_bias = a->lane_bias;
+  kp.residual = static_cast<const bf16*>(a->residual);
+  kp.ldr = a->ldr;
+  kp.out = static_cast<bf16*>(a->out);
+  kp.ldo = a->ldo;
+
+  const int num_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n * kp.num_n_tiles;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  switch (bn_tile) {
+    case 256: return launch_gemm<256>(kp, num_tiles, stream);
+    case 160: return launch_gemm<160>(kp, num_tiles, stream);
+    case 128: return launch_gemm<128>(kp, num_tiles, stream);
+    default: return launch_gemm<64>(kp, num_tiles, stream);
+  }
+}
