@@ -90,7 +90,8 @@ typedef struct sg_gemm_args {
   int32_t mode;
   float res_scale;
   const float* bias;      /* [N] (pre-activation columns) or NULL */
-  const float* lane_bias; /* [out_n, N] or NULL (per-image row bias: time embedding)      */
+  const float* lane_bias; /* [out_n, ld_lane_bias] or NULL (per-image bias: time embedding) */
+  int64_t ld_lane_bias;
   const void* residual;   /* bf16 [M, ldr] or NULL (M = out_n*out_h*out_w rows)           */
   int64_t ldr;
   void* out; /* bf16 [M, ldo] */
@@ -102,7 +103,8 @@ int sg_gemm(const sg_gemm_args* args, void* stream);
 /* ---- fused attention core (FlashAttention-style, tcgen05 + TMEM) -----------------------------
  * o[n, q, h*d:(h+1)*d] = softmax(scale * Q_h K_h^T) V_h for every (n, h); Q/K/V are read in place
  * from (n, token, channel) bf16 tensors with arbitrary row strides (so a fused QKV projection
- * output can be consumed directly).  Image lane n reads K/V lane kv_lane_div ? n / kv_lane_div : n.
+ * output can be consumed directly).  Q lane n reads K/V lane kv_map[n] (identity when NULL), so
+ * CFG lanes that share prior-frame features share one K/V projection.
  *
  * Replaces: CrossAttention core of attn1 / attn2 / attn3 — baddbmm + softmax + bmm or
  * xformers.ops.memory_efficient_attention (model/attention.py:255-260, 271-276, 285-290 via
@@ -117,9 +119,9 @@ typedef struct sg_attn_args {
   int64_t k_stride_n, k_stride_t;
   int64_t v_stride_n, v_stride_t;
   int64_t o_stride_n, o_stride_t;
-  int32_t n_lanes, n_heads, head_dim; /* head_dim in {40, 80, 160} (any multiple of 8 <= 192) */
+  int32_t n_lanes, n_heads, head_dim; /* head_dim in {32, 40, 64, 80, 128, 160} */
   int32_t nq, nk;
-  int32_t n_kv_lanes; /* K/V lanes; lane n uses K/V lane n % n_kv_lanes... see kv_map */
+  int32_t n_kv_lanes;    /* number of K/V lanes (0 = n_lanes)                                  */
   const int32_t* kv_map; /* optional device int32[n_lanes]: K/V lane of each Q lane; NULL = identity */
   float scale;        /* softmax scale (head_dim^-0.5)                                        */
 } sg_attn_args;
@@ -129,14 +131,17 @@ int sg_attention(const sg_attn_args* args, void* stream);
 /* ---- normalisation / elementwise kernels (HBM-bound) ---------------------------------------- */
 
 /* GroupNorm statistics over an NHWC tensor that is the channel-concat of up to two sources.
- * stats[n, g] = (mean, rstd) fp32.  Replaces the reduction half of nn.GroupNorm
+ * `stats` is an fp32 workspace of sg_groupnorm_ws_floats() floats holding fixed-order partial
+ * (sum, sum of squares) per (image, pixel chunk, group); sg_groupnorm_apply finishes the reduction
+ * (deterministic, no atomics).  Replaces the reduction half of nn.GroupNorm
  * (ResnetBlock2D.norm1/norm2, Transformer2DModel.norm model/attention.py:55,98, conv_norm_out
  * model/unet_2d_condition.py:259-262,477-479). */
+int sg_groupnorm_ws_floats(int32_t n_img, int32_t groups); /* size of `stats` in floats */
 int sg_groupnorm_stats(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img,
                        int32_t hw, int32_t groups, float eps, float* stats, void* stream);
 /* y = (x - mean) * rstd * gamma + beta, optionally followed by SiLU; x = concat(x0, x1) along c. */
 int sg_groupnorm_apply(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img,
-                       int32_t hw, int32_t groups, const float* stats, const float* gamma,
+                       int32_t hw, int32_t groups, float eps, const float* stats, const float* gamma,
                        const float* beta, int32_t silu, void* y, void* stream);
 
 /* LayerNorm over the channel dim of a (rows, c) bf16 tensor; up to two affine outputs from one
@@ -145,9 +150,9 @@ int sg_layernorm(const void* x, int64_t rows, int32_t c, float eps, const float*
                  const float* beta_a, void* y_a, const float* gamma_b, const float* beta_b,
                  void* y_b, void* stream);
 
-/* Sinusoidal timestep features [cos | sin] (flip_sin_to_cos=True, freq_shift=0), fp32 -> bf16.
+/* Sinusoidal timestep features [cos | sin] (flip_sin_to_cos=True, freq_shift=0), fp32 (n, dim).
  * Replaces diffusers Timesteps (model/unet_2d_condition.py:392). */
-int sg_timestep_features(const float* t, int32_t n, int32_t dim, void* out_bf16, void* stream);
+int sg_timestep_features(const float* t, int32_t n, int32_t dim, float* out, void* stream);
 
 /* Small dense layers on (n, k) rows where n is the image-lane count (time embedding MLP and the 22
  * time_emb_proj layers): out = act_out(W * act_in(x) + b); x, out fp32; W bf16 [m, k].

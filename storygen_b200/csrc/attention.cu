@@ -217,19 +217,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         m_used = mt;
         need = true;
       }
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-        mbar_wait(o_done, (j - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2 * NA; ++c) {
-          uint32_t ov[32];
-          tmem_ld32(tmem_base + lane_base + Cfg::kColO + c * 32, ov);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-          tmem_st32(tmem_base + lane_base + Cfg::kColO + c * 32, ov);
-        }
-      }
       float sum = 0.f;
       uint32_t pk[2][32];
 #pragma unroll
@@ -242,6 +229,24 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
           pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
         }
       l_run = l_run * alpha + sum;
+      // PV_{j-1} must have retired before P_j overwrites the S/P buffer of tile j-2 and before the O
+      // row may be rescaled.  o_done phases are consumed strictly in order (one wait per tile): an
+      // mbarrier parity wait on a phase that has not started yet would return immediately.
+      if (j > 0) {
+        mbar_wait(o_done, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+          for (int c = 0; c < 2 * NA; ++c) {
+            uint32_t ov[32];
+            tmem_ld32(tmem_base + lane_base + Cfg::kColO + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st32(tmem_base + lane_base + Cfg::kColO + c * 32, ov);
+          }
+        }
+      }
       tmem_st32(s_tmem, pk[0]);
       tmem_st32(s_tmem + 32, pk[1]);
       tmem_st_wait();
@@ -319,7 +324,10 @@ using namespace sg;
 extern "C" int sg_attention(const sg_attn_args* a, void* stream_v) {
   if (a == nullptr || !a->q || !a->k || !a->v || !a->o) return SG_ERR_ARG;
   if (a->nq < 1 || a->nk < 1 || a->n_lanes < 1 || a->n_heads < 1) return SG_ERR_SHAPE;
-  if (a->head_dim != 40 && a->head_dim != 80 && a->head_dim != 160) return SG_ERR_SHAPE;
+  switch (a->head_dim) {
+    case 32: case 40: case 64: case 80: case 128: case 160: break;
+    default: return SG_ERR_SHAPE;
+  }
   if ((reinterpret_cast<uintptr_t>(a->o) & 15) || (a->o_stride_t % 8) || (a->o_stride_n % 8)) return SG_ERR_ALIGN;
   const int C = a->n_heads * a->head_dim;
   const int kv_lanes = a->n_kv_lanes > 0 ? a->n_kv_lanes : a->n_lanes;
@@ -340,8 +348,11 @@ extern "C" int sg_attention(const sg_attn_args* a, void* stream_v) {
   dim3 grid((a->nq + 127) / 128, a->n_heads, a->n_lanes);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   switch (a->head_dim) {
+    case 32: return launch_attn<32>(kp, grid, stream);
     case 40: return launch_attn<40>(kp, grid, stream);
+    case 64: return launch_attn<64>(kp, grid, stream);
     case 80: return launch_attn<80>(kp, grid, stream);
+    case 128: return launch_attn<128>(kp, grid, stream);
     default: return launch_attn<160>(kp, grid, stream);
   }
 }

@@ -1,0 +1,521 @@
+// HBM-bound kernels of the hot path: GroupNorm (two-phase), LayerNorm, timestep embedding + small
+// dense layers, nearest 2x up-sample, conv_in / conv_out (4 channels), add_noise, CFG + DDIM update.
+// All activations are channel-last bf16 and are moved as 16-byte vectors (8 channels); statistics
+// are fp32 and are reduced with warp shuffles + fixed-order partial sums (deterministic).
+#include "common.cuh"
+
+namespace sg {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 q;
+  q.x = pack_bf16x2(f[0], f[1]); q.y = pack_bf16x2(f[2], f[3]);
+  q.z = pack_bf16x2(f[4], f[5]); q.w = pack_bf16x2(f[6], f[7]);
+  return q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm
+// ------------------------------------------------------------------------------------------------
+constexpr int kGnMaxChunks = 32;
+__host__ __device__ inline int gn_chunks(int hw) {
+  int c = hw / 128;
+  return c < 1 ? 1 : (c > kGnMaxChunks ? kGnMaxChunks : c);
+}
+// block = V * PS threads: V = C/8 channel vectors, PS pixel lanes
+static inline void gn_block_shape(int C, int* V, int* PS) {
+  *V = C / 8;
+  int ps = 320 / *V;
+  *PS = ps < 1 ? 1 : ps;
+}
+
+// partial[n][chunk][group][2] = (sum, sumsq) over the chunk's pixels
+__global__ void gn_stats_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1, int c1, int hw,
+                                int groups, float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [PS][C][2]
+  const int C = c0 + c1, V = C / 8, PS = blockDim.x / V;
+  const int v = threadIdx.x % V, pl = threadIdx.x / V;
+  const int chunks = gridDim.x, chunk = blockIdx.x, n = blockIdx.y;
+  const int p_begin = static_cast<int>(static_cast<long long>(hw) * chunk / chunks);
+  const int p_end = static_cast<int>(static_cast<long long>(hw) * (chunk + 1) / chunks);
+  const bool from0 = (v * 8 < c0);
+  const bf16* base = from0 ? x0 + static_cast<long long>(n) * hw * c0 + v * 8
+                           : x1 + static_cast<long long>(n) * hw * c1 + (v * 8 - c0);
+  const int cs = from0 ? c0 : c1;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  for (int p = p_begin + pl; p < p_end; p += PS) {
+    uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p) * cs));
+    float f[8];
+    unpack8(raw, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i] += f[i];
+      q[i] += f[i] * f[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sm[(pl * C + v * 8 + i) * 2 + 0] = s[i];
+    sm[(pl * C + v * 8 + i) * 2 + 1] = q[i];
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float ts = 0.f, tq = 0.f;
+    for (int pp = 0; pp < PS; ++pp)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        ts += sm[(pp * C + c) * 2 + 0];
+        tq += sm[(pp * C + c) * 2 + 1];
+      }
+    float* dst = partial + ((static_cast<long long>(n) * chunks + chunk) * groups + g) * 2;
+    dst[0] = ts;
+    dst[1] = tq;
+  }
+}
+
+__global__ void gn_apply_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1, int c1, int hw,
+                                int groups, int chunks, float eps, const float* __restrict__ partial,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                bf16* __restrict__ y) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int C = c0 + c1, V = C / 8, PS = blockDim.x / V;
+  const int v = threadIdx.x % V, pl = threadIdx.x / V;
+  const int n = blockIdx.y;
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float ts = 0.f, tq = 0.f;
+    for (int ch = 0; ch < chunks; ++ch) {
+      const float* src = partial + ((static_cast<long long>(n) * chunks + ch) * groups + g) * 2;
+      ts += src[0];
+      tq += src[1];
+    }
+    const float cnt = static_cast<float>(hw) * cpg;
+    const float mean = ts / cnt;
+    const float var = fmaxf(tq / cnt - mean * mean, 0.f);
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int slabs = gridDim.x, slab = blockIdx.x;
+  const int p_begin = static_cast<int>(static_cast<long long>(hw) * slab / slabs);
+  const int p_end = static_cast<int>(static_cast<long long>(hw) * (slab + 1) / slabs);
+  const bool from0 = (v * 8 < c0);
+  const bf16* base = from0 ? x0 + static_cast<long long>(n) * hw * c0 + v * 8
+                           : x1 + static_cast<long long>(n) * hw * c1 + (v * 8 - c0);
+  const int cs = from0 ? c0 : c1;
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = v * 8 + i;
+    const int g = c / cpg;
+    const float ga = gamma[c] * s_rstd[g];
+    a[i] = ga;
+    b[i] = beta[c] - s_mean[g] * ga;
+  }
+  bf16* ybase = y + static_cast<long long>(n) * hw * C + v * 8;
+  for (int p = p_begin + pl; p < p_end; p += PS) {
+    uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p) * cs));
+    float f[8];
+    unpack8(raw, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = fmaf(f[i], a[i], b[i]);
+      f[i] = silu ? silu_f(t) : t;
+    }
+    *reinterpret_cast<uint4*>(ybase + static_cast<long long>(p) * C) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers (C <= 1280), two affine outputs
+// ------------------------------------------------------------------------------------------------
+template <int MAXV>  // vectors of 8 per lane
+__global__ void layernorm_kernel(const bf16* __restrict__ x, long long rows, int C, float eps,
+                                 const float* __restrict__ ga, const float* __restrict__ ba, bf16* __restrict__ ya,
+                                 const float* __restrict__ gb, const float* __restrict__ bb, bf16* __restrict__ yb) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int V = C / 8;
+  const bf16* xr = x + row * C;
+  float f[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+      uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+      unpack8(raw, f[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += f[i][k];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = f[i][k] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+      float o[8];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(ga + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(ga + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(ba + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(ba + v * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (f[i][k] - mean) * rstd * gg[k] + bv[k];
+      *reinterpret_cast<uint4*>(ya + row * C + v * 8) = pack8(o);
+      if (yb != nullptr) {
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(gb + v * 8));
+        const float4 h1 = __ldg(reinterpret_cast<const float4*>(gb + v * 8 + 4));
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(bb + v * 8));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(bb + v * 8 + 4));
+        const float hg[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const float hb[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (f[i][k] - mean) * rstd * hg[k] + hb[k];
+        *reinterpret_cast<uint4*>(yb + row * C + v * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// timestep embedding
+// ------------------------------------------------------------------------------------------------
+__global__ void timestep_features_kernel(const float* __restrict__ t, int n, int dim, float* __restrict__ out) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * half) return;
+  const int i = idx % half, r = idx / half;
+  // exponent = -ln(10000) * i / half   (downscale_freq_shift = 0)
+  const float freq = expf(-9.210340371976184f * static_cast<float>(i) / static_cast<float>(half));
+  const float arg = t[r] * freq;
+  out[r * dim + i] = cosf(arg);          // flip_sin_to_cos=True -> [cos | sin]
+  out[r * dim + half + i] = sinf(arg);
+}
+
+// out[r][m] = act_out( sum_k W[m][k] * act_in(x[r][k]) + b[m] ); one warp per output feature m.
+__global__ void small_linear_kernel(const float* __restrict__ x, int n, int k, const bf16* __restrict__ w,
+                                    const float* __restrict__ b, int m, int silu_in, int silu_out,
+                                    float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= m) return;
+  const bf16* wr = w + static_cast<long long>(row) * k;
+  const int V = k / 8;
+  for (int r = 0; r < n; ++r) {
+    float acc = 0.f;
+    for (int v = lane; v < V; v += 32) {
+      float wf[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(wr + v * 8)), wf);
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r) * k + v * 8));
+      const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r) * k + v * 8 + 4));
+      float xf[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xv = silu_in ? silu_f(xf[i]) : xf[i];
+        acc = fmaf(wf[i], xv, acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float y = acc + (b ? b[row] : 0.f);
+      out[static_cast<long long>(r) * m + row] = silu_out ? silu_f(y) : y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// up-sample, conv_in, conv_out
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, int n, int h, int w, int v /*C/8*/,
+                                  uint4* __restrict__ y) {
+  const long long total = static_cast<long long>(n) * (2 * h) * (2 * w) * v;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vc = static_cast<int>(i % v);
+    long long p = i / v;
+    const int ox = static_cast<int>(p % (2 * w));
+    p /= (2 * w);
+    const int oy = static_cast<int>(p % (2 * h));
+    const int nn = static_cast<int>(p / (2 * h));
+    y[i] = __ldg(x + ((static_cast<long long>(nn) * h + (oy >> 1)) * w + (ox >> 1)) * v + vc);
+  }
+}
+
+// thread = (pixel, 8 output channels); weights [cout][cin][3][3] fp32
+__global__ void conv_in_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
+                               const float* __restrict__ wgt, const float* __restrict__ bias, int cout,
+                               bf16* __restrict__ y) {
+  const int V = cout / 8;
+  const long long total = static_cast<long long>(n) * h * w * V;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int vc = static_cast<int>(i % V);
+  long long p = i / V;
+  const int px = static_cast<int>(p % w);
+  p /= w;
+  const int py = static_cast<int>(p % h);
+  const int nn = static_cast<int>(p / h);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = bias[vc * 8 + k];
+  for (int ci = 0; ci < cin; ++ci)
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = py + ky - 1;
+      if (yy < 0 || yy >= h) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = px + kx - 1;
+        if (xx < 0 || xx >= w) continue;
+        const float xv = x[((static_cast<long long>(nn) * cin + ci) * h + yy) * w + xx];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          acc[k] = fmaf(xv, __ldg(wgt + ((static_cast<long long>(vc * 8 + k) * cin + ci) * 3 + ky) * 3 + kx), acc[k]);
+      }
+    }
+  *reinterpret_cast<uint4*>(y + ((static_cast<long long>(nn) * h + py) * w + px) * cout + vc * 8) = pack8(acc);
+}
+
+// one warp per output pixel; weights [cout][cin][3][3] fp32 re-laid in smem as [tap][cout][cin]
+__global__ void conv_out_kernel(const bf16* __restrict__ x, int n, int cin, int h, int w,
+                                const float* __restrict__ wgt, const float* __restrict__ bias, int cout,
+                                float* __restrict__ y) {
+  extern __shared__ float ws[];  // [9][cout][cin]
+  for (int i = threadIdx.x; i < 9 * cout * cin; i += blockDim.x) {
+    const int ci = i % cin;
+    const int co = (i / cin) % cout;
+    const int tap = i / (cin * cout);
+    ws[i] = wgt[(static_cast<long long>(co) * cin + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long pix = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= static_cast<long long>(n) * h * w) return;
+  const int px = static_cast<int>(pix % w);
+  const int py = static_cast<int>((pix / w) % h);
+  const int nn = static_cast<int>(pix / (static_cast<long long>(w) * h));
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const int V = cin / 8;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky - 1;
+    if (yy < 0 || yy >= h) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = px + kx - 1;
+      if (xx < 0 || xx >= w) continue;
+      const bf16* xp = x + ((static_cast<long long>(nn) * h + yy) * w + xx) * cin;
+      const float* wt = ws + (ky * 3 + kx) * cout * cin;
+      for (int v = lane; v < V; v += 32) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(xp + v * 8)), f);
+#pragma unroll
+        for (int co = 0; co < 8; ++co) {
+          if (co < cout) {
+            const float* wc = wt + co * cin + v * 8;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[co] = fmaf(f[k], wc[k], acc[co]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 8; ++co) {
+    if (co < cout) {
+      float a = acc[co];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) y[((static_cast<long long>(nn) * cout + co) * h + py) * w + px] = a + bias[co];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// scheduler arithmetic
+// ------------------------------------------------------------------------------------------------
+__global__ void add_noise_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                 const float* __restrict__ acp, const int* __restrict__ t, int n, int chw,
+                                 float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(n) * chw) return;
+  const int r = static_cast<int>(i / chw);
+  const float a = acp[t[r]];
+  out[i] = sqrtf(a) * x[i] + sqrtf(1.0f - a) * eps[i];
+}
+
+__global__ void cfg_ddim_kernel(const float* __restrict__ eps3, float* __restrict__ lat, long long total,
+                                float s_img, float s_txt, float alpha_t, float alpha_prev) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float u = eps3[i], im = eps3[total + i], al = eps3[2 * total + i];
+  const float e = u + s_img * (im - u) + s_txt * (al - im);
+  const float x = lat[i];
+  const float x0 = (x - sqrtf(1.0f - alpha_t) * e) / sqrtf(alpha_t);
+  lat[i] = sqrtf(alpha_prev) * x0 + sqrtf(1.0f - alpha_prev) * e;
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+#define SG_LAUNCH_END()   \
+  count_launch();         \
+  return static_cast<int>(cudaGetLastError())
+
+extern "C" int sg_groupnorm_ws_floats(int32_t n_img, int32_t groups) { return n_img * groups * 2 * kGnMaxChunks; }
+
+extern "C" int sg_groupnorm_stats(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img,
+                                  int32_t hw, int32_t groups, float eps, float* stats, void* stream) {
+  (void)eps;
+  const int C = c0 + c1;
+  if (!x0 || !stats || (c1 > 0 && !x1)) return SG_ERR_ARG;
+  if (C % 8 || c0 % 8 || C % groups || groups > 64 || C / 8 > 1024) return SG_ERR_SHAPE;
+  int V, PS;
+  gn_block_shape(C, &V, &PS);
+  const int chunks = gn_chunks(hw);
+  const size_t smem = static_cast<size_t>(PS) * C * 2 * sizeof(float);
+  gn_stats_kernel<<<dim3(chunks, n_img), V * PS, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x0), c0, static_cast<const bf16*>(x1), c1, hw, groups, stats);
+  SG_LAUNCH_END();
+}
+
+extern "C" int sg_groupnorm_apply(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img,
+                                  int32_t hw, int32_t groups, float eps, const float* stats, const float* gamma,
+                                  const float* beta, int32_t silu, void* y, void* stream) {
+  const int C = c0 + c1;
+  if (!x0 || !stats || !gamma || !beta || !y || (c1 > 0 && !x1)) return SG_ERR_ARG;
+  if (C % 8 || c0 % 8 || C % groups || groups > 64 || C / 8 > 1024) return SG_ERR_SHAPE;
+  int V, PS;
+  gn_block_shape(C, &V, &PS);
+  const int chunks = gn_chunks(hw);
+  int slabs = hw / (PS * 4);
+  slabs = slabs < 1 ? 1 : (slabs > 64 ? 64 : slabs);
+  gn_apply_kernel<<<dim3(slabs, n_img), V * PS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x0), c0, static_cast<const bf16*>(x1), c1, hw, groups, chunks, eps, stats, gamma,
+      beta, silu, static_cast<bf16*>(y));
+  SG_LAUNCH_END();
+}
+
+extern "C" int sg_layernorm(const void* x, int64_t rows, int32_t c, float eps, const float* gamma_a,
+                            const float* beta_a, void* y_a, const float* gamma_b, const float* beta_b, void* y_b,
+                            void* stream) {
+  if (!x || !gamma_a || !beta_a || !y_a) return SG_ERR_ARG;
+  if (y_b && (!gamma_b || !beta_b)) return SG_ERR_ARG;
+  if (c % 8 || c > 1280) return SG_ERR_SHAPE;
+  const int warps = 8;
+  const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bf16* xp = static_cast<const bf16*>(x);
+  bf16* ya = static_cast<bf16*>(y_a);
+  bf16* yb = static_cast<bf16*>(y_b);
+  if (c <= 512)
+    layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(xp, rows, c, eps, gamma_a, beta_a, ya, gamma_b, beta_b, yb);
+  else if (c <= 768)
+    layernorm_kernel<3><<<grid, warps * 32, 0, st>>>(xp, rows, c, eps, gamma_a, beta_a, ya, gamma_b, beta_b, yb);
+  else
+    layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(xp, rows, c, eps, gamma_a, beta_a, ya, gamma_b, beta_b, yb);
+  SG_LAUNCH_END();
+}
+
+extern "C" int sg_timestep_features(const float* t, int32_t n, int32_t dim, float* out, void* stream) {
+  if (!t || !out) return SG_ERR_ARG;
+  if (dim % 2) return SG_ERR_SHAPE;
+  const int total = n * dim / 2;
+  timestep_features_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, n, dim, out);
+  SG_LAUNCH_END();
+}
+
+extern "C" int sg_small_linear(const float* x, int32_t n, int32_t k, const void* w, const float* b, int32_t m,
+                               int32_t silu_in, int32_t silu_out, float* out, void* stream) {
+  if (!x || !w || !out) return SG_ERR_ARG;
+  if (k % 8) return SG_ERR_SHAPE;
+  small_linear_kernel<<<(m + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n, k, static_cast<const bf16*>(w), b, m, silu_in, silu_out, out);
+  SG_LAUNCH_END();
+}
+
+extern "C" int sg_upsample2x(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream) {
+  if (!x || !y) return SG_ERR_ARG;
+  if (c % 8) return SG_ERR_SHAPE;
+  const long long total = static_cast<long long>(n) * 4 * h * w * (c / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), n, h, w, c / 8, static_cast<uint4*>(y));
+  SG_LAUNCH_END();
+}
+
+extern "C" int sg_conv_in(const float* x_nchw, int32_t n, int32_t cin, int32_t h, int32_t w, const float* wgt,
+                          const float* bias, int32_t cout, void* y_nhwc, void* stream) {
+  if (!x_nchw || !wgt || !bias || !y_nhwc) return SG_ERR_ARG;
+  if (cout % 8) return SG_ERR_SHAPE;
+  const long long total = static_cast<long long>(n) * h * w * (cout / 8);
+  conv_in_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, n, cin, h, w, wgt, bias, cout, static_cast<bf16*>(y_nhwc));
+  SG_LAUNCH_END();
+}
+
+extern "C" int sg_conv_out(const void* x_nhwc, int32_t n, int32_t cin, int32_t h, int32_t w, const float* wgt,
+                           const float* bias, int32_t cout, float* y_nchw, void* stream) {
+  if (!x_nhwc || !wgt || !bias || !y_nchw) return SG_ERR_ARG;
+  if (cin % 8 || cout > 8) return SG_ERR_SHAPE;
+  const size_t smem = static_cast<size_t>(9) * cout * cin * sizeof(float);
+  if (smem > 200 * 1024) return SG_ERR_SHAPE;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const long long pixels = static_cast<long long>(n) * h * w;
+  const int warps = 16;
+  conv_out_kernel<<<static_cast<unsigned>((pixels + warps - 1) / warps), warps * 32, smem,
+                    static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x_nhwc), n, cin, h, w, wgt, bias,
+                                                         cout, y_nchw);
+  SG_LAUNCH_END();
+}
+
+extern "C" int sg_add_noise(const float* x, const float* eps, const float* acp, const int32_t* t, int32_t n,
+                            int32_t chw, float* out, void* stream) {
+  if (!x || !eps || !acp || !t || !out) return SG_ERR_ARG;
+  const long long total = static_cast<long long>(n) * chw;
+  add_noise_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, eps, acp, t, n, chw, out);
+  SG_LAUNCH_END();
+}
+
+extern "C" int sg_cfg_ddim_step(const float* eps3, float* latents, int32_t b, int32_t chw, float s_img,
+                                float s_txt, float alpha_t, float alpha_prev, void* stream) {
+  if (!eps3 || !latents) return SG_ERR_ARG;
+  const long long total = static_cast<long long>(b) * chw;
+  cfg_ddim_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      eps3, latents, total, s_img, s_txt, alpha_t, alpha_prev);
+  SG_LAUNCH_END();
+}

@@ -33,6 +33,7 @@ struct GemmKParams {
   float res_scale;
   const float* bias;
   const float* lane_bias;
+  long long ld_lane_bias;
   const bf16* residual;
   long long ldr;
   bf16* out;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           }
           if (p.lane_bias != nullptr) {
             const float4* b4 =
-                reinterpret_cast<const float4*>(p.lane_bias + static_cast<long long>(n) * p.N + col0);
+                reinterpret_cast<const float4*>(p.lane_bias + static_cast<long long>(n) * p.ld_lane_bias + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 b = __ldg(b4 + j);
@@ -361,6 +362,7 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   kp.res_scale = a->res_scale;
   kp.bias = a->bias;
   kp.lane_bias = a->lane_bias;
+  kp.ld_lane_bias = a->ld_lane_bias > 0 ? a->ld_lane_bias : a->N;
   kp.residual = static_cast<const bf16*>(a->residual);
   kp.ldr = a->ldr;
   kp.out = static_cast<bf16*>(a->out);
