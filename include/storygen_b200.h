@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 3
+#define SG_ABI_VERSION 4
 
 #define SG_ERR_SHAPE (-1)   /* unsupported / inconsistent shape            */
 #define SG_ERR_ALIGN (-2)   /* pointer or stride not 16-byte aligned        */
@@ -179,9 +179,10 @@ int sg_add_noise(const float* x, const float* eps, const float* acp, const int32
 /* Dual classifier-free guidance + eta=0 DDIM update (model/pipeline.py:456-461):
  *   e = u + s_img (i - u) + s_txt (a - i);  x0 = (x - sqrt(1-a_t) e)/sqrt(a_t);
  *   x' = sqrt(a_prev) x0 + sqrt(1 - a_prev) e.
- * eps3 = (3, b, chw) lanes [uncond | image | all]; latents updated in place. */
+ * eps3 = (3, b, chw) lanes [uncond | image | all]; latents updated in place; `alphas` is a DEVICE
+ * pair (a_t, a_prev) so a captured CUDA graph of one step can be replayed for every timestep. */
 int sg_cfg_ddim_step(const float* eps3, float* latents, int32_t b, int32_t chw, float s_img,
-                     float s_txt, float alpha_t, float alpha_prev, void* stream);
+                     float s_txt, const float* alphas, void* stream);
 
 #ifdef __cplusplus
 }

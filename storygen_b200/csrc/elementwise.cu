@@ -371,9 +371,10 @@ __global__ void add_noise_kernel(const float* __restrict__ x, const float* __res
 }
 
 __global__ void cfg_ddim_kernel(const float* __restrict__ eps3, float* __restrict__ lat, long long total,
-                                float s_img, float s_txt, float alpha_t, float alpha_prev) {
+                                float s_img, float s_txt, const float* __restrict__ alphas) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  const float alpha_t = alphas[0], alpha_prev = alphas[1];
   const float u = eps3[i], im = eps3[total + i], al = eps3[2 * total + i];
   const float e = u + s_img * (im - u) + s_txt * (al - im);
   const float x = lat[i];
@@ -512,10 +513,10 @@ extern "C" int sg_add_noise(const float* x, const float* eps, const float* acp, 
 }
 
 extern "C" int sg_cfg_ddim_step(const float* eps3, float* latents, int32_t b, int32_t chw, float s_img,
-                                float s_txt, float alpha_t, float alpha_prev, void* stream) {
-  if (!eps3 || !latents) return SG_ERR_ARG;
+                                float s_txt, const float* alphas, void* stream) {
+  if (!eps3 || !latents || !alphas) return SG_ERR_ARG;
   const long long total = static_cast<long long>(b) * chw;
   cfg_ddim_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      eps3, latents, total, s_img, s_txt, alpha_t, alpha_prev);
+      eps3, latents, total, s_img, s_txt, alphas);
   SG_LAUNCH_END();
 }

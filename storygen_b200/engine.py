@@ -1,0 +1,338 @@
+"""Executes UNet2DConditionModel.forward with the sm_100a kernels.
+
+Data layout: every activation is channel-last bf16 — images (n, y, x, c), token streams (n, token, c);
+the two are the same memory, so the reference's NCHW<->token permutes around each transformer
+(model/attention.py:103,117) do not exist here.  Weights are re-packed once per model (bf16, K-major,
+conv taps / shortcut / fused projections concatenated along K or N as the kernels consume them).
+
+Launch sequence per ResnetBlock2D (6 kernels):
+    gn_stats, gn_apply+SiLU(+channel concat) -> conv3x3 GEMM (+bias +time embedding)
+    gn_stats, gn_apply+SiLU                  -> conv3x3 GEMM (+1x1 shortcut as extra K segments | +x)
+per Transformer2DModel (feature pass 17, denoise pass 20 kernels):
+    GN -> proj_in GEMM -> LN1 -> QKV GEMM -> attention -> out-proj GEMM(+h) [= the tapped feature]
+    LN2(/LN4) -> Q GEMM, text KV GEMM, attention [-> Q3 GEMM, image KV GEMM, attention]
+    out-proj GEMM over [a_text | a_image] (+2h)  -> LN3 -> FF1 GEMM(GEGLU) -> FF2 GEMM(+h) -> proj_out GEMM(+x)
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from ._lib import SG_EPI_GEGLU
+from .ops import BF16, Src, taps3x3
+
+F32 = torch.float32
+
+
+class UNetEngine:
+    def __init__(self, model):
+        self.model = model
+        p = next(model.parameters())
+        if p.device.type != "cuda":
+            raise RuntimeError("storygen_b200.UNet2DConditionModel runs only on a CUDA (sm_100a) device: move the "
+                               "model with .to('cuda') first (there is no CPU fallback)")
+        self.dev = p.device
+        cfg = model.config
+        self.groups = cfg.norm_num_groups
+        self.eps = cfg.norm_eps
+        self.heads = cfg.attention_head_dim
+        self.boc = tuple(cfg.block_out_channels)
+        self.temb_dim = self.boc[0] * 4
+        for c in self.boc:
+            if c % 64 or (c // self.heads) not in (32, 40, 64, 80, 128, 160):
+                raise NotImplementedError(f"block_out_channels {self.boc} / heads {self.heads}: channel counts must be "
+                                          "multiples of 64 with head dim in {32,40,64,80,128,160}")
+        if cfg.cross_attention_dim % 64:
+            raise NotImplementedError("cross_attention_dim must be a multiple of 64")
+        self._pack()
+        self._stats = None
+
+    # ------------------------------------------------------------------------------------------
+    # weight packing
+    # ------------------------------------------------------------------------------------------
+    def _bf(self, t):
+        return t.detach().to(self.dev, BF16).contiguous()
+
+    def _f32(self, t):
+        return t.detach().to(self.dev, F32).contiguous()
+
+    def _conv3(self, w):  # [co, ci, 3, 3] -> [co, (ky, kx, ci)]
+        return w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+    def _pack_resnet(self, r, temb_w: List, temb_b: List):
+        d = dict(cin=r.in_channels, cout=r.out_channels)
+        d["gn1"] = (self._f32(r.norm1.weight), self._f32(r.norm1.bias))
+        d["gn2"] = (self._f32(r.norm2.weight), self._f32(r.norm2.bias))
+        d["w1"] = self._bf(self._conv3(r.conv1.weight))
+        d["temb_off"] = sum(w.shape[0] for w in temb_w)
+        temb_w.append(r.time_emb_proj.weight.detach())
+        temb_b.append(r.time_emb_proj.bias.detach() + r.conv1.bias.detach())  # conv1 bias folded in
+        w2 = self._conv3(r.conv2.weight)
+        b2 = r.conv2.bias.detach()
+        if r.conv_shortcut is not None:
+            w2 = torch.cat([w2, r.conv_shortcut.weight.detach().reshape(r.out_channels, r.in_channels)], dim=1)
+            b2 = b2 + r.conv_shortcut.bias.detach()
+        d["w2"], d["b2"], d["shortcut"] = self._bf(w2), self._f32(b2), r.conv_shortcut is not None
+        return d
+
+    def _pack_transformer(self, t):
+        blk = t.transformer_blocks[0]
+        c = t.proj_in.weight.shape[0]
+        ln = lambda m: (self._f32(m.weight), self._f32(m.bias))
+        d = dict(c=c, heads=t.num_attention_heads, hd=t.attention_head_dim)
+        d["gn"] = (self._f32(t.norm.weight), self._f32(t.norm.bias))
+        d["w_in"], d["b_in"] = self._bf(t.proj_in.weight.reshape(c, -1)), self._f32(t.proj_in.bias)
+        d["w_out"], d["b_out"] = self._bf(t.proj_out.weight.reshape(t.proj_out.weight.shape[0], -1)), self._f32(t.proj_out.bias)
+        d["ln1"], d["ln2"], d["ln3"], d["ln4"] = ln(blk.norm1), ln(blk.norm2), ln(blk.norm3), ln(blk.norm4)
+        a1, a2, a3 = blk.attn1, blk.attn2, blk.attn3
+        d["w_qkv1"] = self._bf(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0))
+        d["w_o1"], d["b_o1"] = self._bf(a1.to_out[0].weight), self._f32(a1.to_out[0].bias)
+        d["w_q2"] = self._bf(a2.to_q.weight)
+        d["w_kv2"] = self._bf(torch.cat([a2.to_k.weight, a2.to_v.weight], 0))
+        d["w_o2"], d["b_o2"] = self._bf(a2.to_out[0].weight), self._f32(a2.to_out[0].bias)
+        d["w_q3"] = self._bf(a3.to_q.weight)
+        d["w_kv3"] = self._bf(torch.cat([a3.to_k.weight, a3.to_v.weight], 0))
+        d["w_o23"] = self._bf(torch.cat([a2.to_out[0].weight, a3.to_out[0].weight], 1))
+        d["b_o23"] = self._f32(a2.to_out[0].bias.detach() + a3.to_out[0].bias.detach())
+        # GEGLU: interleave [16 value rows | 16 gate rows] so one 32-column epilogue chunk holds both halves
+        w, b = blk.ff.net[0].proj.weight.detach(), blk.ff.net[0].proj.bias.detach()
+        half = w.shape[0] // 2
+        d["w_ff1"] = self._bf(torch.stack([w[:half].reshape(-1, 16, c), w[half:].reshape(-1, 16, c)], 1).reshape(2 * half, c))
+        d["b_ff1"] = self._f32(torch.stack([b[:half].reshape(-1, 16), b[half:].reshape(-1, 16)], 1).reshape(-1))
+        d["w_ff2"], d["b_ff2"] = self._bf(blk.ff.net[2].weight), self._f32(blk.ff.net[2].bias)
+        return d
+
+    def _pack(self):
+        m = self.model
+        tw, tb = [], []
+        self.conv_in = (self._f32(m.conv_in.weight), self._f32(m.conv_in.bias))
+        te = m.time_embedding
+        self.time = (self._bf(te.linear_1.weight), self._f32(te.linear_1.bias), self._bf(te.linear_2.weight),
+                     self._f32(te.linear_2.bias))
+        self.down = []
+        for blk in m.down_blocks:
+            d = dict(res=[self._pack_resnet(r, tw, tb) for r in blk.resnets])
+            d["attn"] = [self._pack_transformer(t) for t in blk.attentions] if blk.has_cross_attention else None
+            if blk.downsamplers is not None:
+                cv = blk.downsamplers[0].conv
+                d["down"] = (self._bf(self._conv3(cv.weight)), self._f32(cv.bias))
+            else:
+                d["down"] = None
+            self.down.append(d)
+        mb = m.mid_block
+        self.mid = dict(res=[self._pack_resnet(r, tw, tb) for r in mb.resnets],
+                        attn=[self._pack_transformer(t) for t in mb.attentions])
+        self.up = []
+        for blk in m.up_blocks:
+            d = dict(res=[self._pack_resnet(r, tw, tb) for r in blk.resnets])
+            d["attn"] = [self._pack_transformer(t) for t in blk.attentions] if blk.has_cross_attention else None
+            if blk.upsamplers is not None:
+                cv = blk.upsamplers[0].conv
+                d["up"] = (self._bf(self._conv3(cv.weight)), self._f32(cv.bias))
+            else:
+                d["up"] = None
+            self.up.append(d)
+        self.temb_w = self._bf(torch.cat(tw, 0))
+        self.temb_b = self._f32(torch.cat(tb, 0))
+        self.norm_out = (self._f32(m.conv_norm_out.weight), self._f32(m.conv_norm_out.bias))
+        self.conv_out = (self._f32(m.conv_out.weight), self._f32(m.conv_out.bias))
+
+    # ------------------------------------------------------------------------------------------
+    # building blocks
+    # ------------------------------------------------------------------------------------------
+    def _new(self, *shape, dtype=BF16):
+        return torch.empty(shape, dtype=dtype, device=self.dev)
+
+    def _gn(self, x0, x1, n, hw, gamma_beta, eps, silu):
+        c = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+        out = self._new(n, hw, c)
+        ops.groupnorm(x0, x1, n, hw, self.groups, eps, gamma_beta[0], gamma_beta[1], silu, out, self._stats)
+        return out
+
+    def _resnet(self, p, x0, x1, n, h, w, lane_bias):
+        """x = concat_c(x0, x1) as (n, h, w, c*) tensors.  Returns (n, h, w, cout)."""
+        hw, cout = h * w, p["cout"]
+        xn = self._gn(x0.view(n, hw, -1), None if x1 is None else x1.view(n, hw, -1), n, hw, p["gn1"], self.eps, True)
+        h1 = self._new(n, h, w, cout)
+        ops.gemm([Src.nhwc(xn.view(n, h, w, -1))], taps3x3(0, p["cin"]), (w, h, n), p["w1"], h1,
+                 lane_bias=lane_bias[:, p["temb_off"]:], ld_lane_bias=lane_bias.shape[1])
+        hn = self._gn(h1.view(n, hw, cout), None, n, hw, p["gn2"], self.eps, True)
+        out = self._new(n, h, w, cout)
+        srcs = [Src.nhwc(hn.view(n, h, w, cout))]
+        segs = taps3x3(0, cout)
+        residual = None
+        if p["shortcut"]:
+            srcs.append(Src.nhwc(x0))
+            segs.append((1, 0, 0, 0, x0.shape[-1] // 64))
+            if x1 is not None:
+                srcs.append(Src.nhwc(x1))
+                segs.append((2, 0, 0, 0, x1.shape[-1] // 64))
+        else:
+            residual = x0
+        ops.gemm(srcs, segs, (w, h, n), p["w2"], out, bias=p["b2"], residual=residual)
+        return out
+
+    def _transformer(self, p, x, n, h, w, text, n_text_tokens, image, kv_map, n_kv_lanes):
+        """x (n, h, w, c); text (n * L, D) bf16; image None or (n_kv, R*hw, c) bf16.
+        Returns (out (n, h, w, c), tap (n, hw, c))."""
+        hw, c, heads, hd = h * w, p["c"], p["heads"], p["hd"]
+        m = n * hw
+        xn = self._gn(x.view(n, hw, c), None, n, hw, p["gn"], 1e-6, False)
+        h0 = self._new(m, c)
+        ops.linear(xn.view(m, c), p["w_in"], h0, bias=p["b_in"])
+        # --- self attention
+        n1 = self._new(m, c)
+        ops.layernorm(h0, 1e-5, p["ln1"][0], p["ln1"][1], n1)
+        qkv = self._new(m, 3 * c)
+        ops.linear(n1, p["w_qkv1"], qkv)
+        a1 = self._new(m, c)
+        st = (hw * 3 * c, 3 * c)
+        ops.attention(qkv, qkv[:, c:], qkv[:, 2 * c:], a1, n, heads, hd, hw, hw, st, st, st)
+        h1 = self._new(m, c)  # residual stream after self-attention == the tapped diffusion feature
+        ops.linear(a1, p["w_o1"], h1, bias=p["b_o1"], residual=h0)
+        # --- text (+ image) cross attention
+        n2 = self._new(m, c)
+        n4 = self._new(m, c) if image is not None else None
+        if image is not None:
+            ops.layernorm(h1, 1e-5, p["ln2"][0], p["ln2"][1], n2, p["ln4"][0], p["ln4"][1], n4)
+        else:
+            ops.layernorm(h1, 1e-5, p["ln2"][0], p["ln2"][1], n2)
+        q2 = self._new(m, c)
+        ops.linear(n2, p["w_q2"], q2)
+        L = n_text_tokens
+        kv2 = self._new(n * L, 2 * c)
+        ops.linear(text, p["w_kv2"], kv2)
+        a2 = self._new(m, c)
+        ops.attention(q2, kv2, kv2[:, c:], a2, n, heads, hd, hw, L, (hw * c, c), (L * 2 * c, 2 * c), (L * 2 * c, 2 * c))
+        h2 = self._new(m, c)
+        if image is not None:
+            q3 = self._new(m, c)
+            ops.linear(n4, p["w_q3"], q3)
+            nkv, nk = image.shape[0], image.shape[1]
+            kv3 = self._new(nkv * nk, 2 * c)
+            ops.linear(image.view(nkv * nk, c), p["w_kv3"], kv3)
+            a3 = self._new(m, c)
+            ops.attention(q3, kv3, kv3[:, c:], a3, n, heads, hd, hw, nk, (hw * c, c), (nk * 2 * c, 2 * c),
+                          (nk * 2 * c, 2 * c), n_kv_lanes=nkv, kv_map=kv_map)
+            # h_t + h_i = 2h + a_t + a_i  (model/attention.py:277,291,293): one GEMM over K = [a2 | a3]
+            ops.gemm([Src.rows(a2), Src.rows(a3)], [(0, 0, 0, 0, c // 64), (1, 0, 0, 0, c // 64)], (m, 1, 1),
+                     p["w_o23"], h2, bias=p["b_o23"], residual=h1, res_scale=2.0)
+        else:
+            ops.linear(a2, p["w_o2"], h2, bias=p["b_o2"], residual=h1)
+        # --- feed forward
+        n3 = self._new(m, c)
+        ops.layernorm(h2, 1e-5, p["ln3"][0], p["ln3"][1], n3)
+        ff = self._new(m, 4 * c)
+        ops.linear(n3, p["w_ff1"], ff, bias=p["b_ff1"], mode=SG_EPI_GEGLU)
+        h3 = self._new(m, c)
+        ops.linear(ff, p["w_ff2"], h3, bias=p["b_ff2"], residual=h2)
+        out = self._new(n, h, w, x.shape[-1])
+        ops.linear(h3, p["w_out"], out.view(m, -1), bias=p["b_out"], residual=x.view(m, -1))
+        return out, h1.view(n, hw, c)
+
+    def _downsample(self, wb, x, n, h, w):
+        c = x.shape[-1]
+        out = self._new(n, h // 2, w // 2, c)
+        srcs = [Src.nhwc_phase(x, py, px) for py in range(2) for px in range(2)]
+        # input row 2*oy + ky - 1: ky=0 -> odd phase shifted by -1, ky=1 -> even phase, ky=2 -> odd phase
+        ph, sh = (1, 0, 1), (-1, 0, 0)
+        segs = [(ph[ky] * 2 + ph[kx], sh[kx], sh[ky], 0, c // 64) for ky in range(3) for kx in range(3)]
+        ops.gemm(srcs, segs, (w // 2, h // 2, n), wb[0], out, bias=wb[1])
+        return out
+
+    def _upsample(self, wb, x, n, h, w):
+        c = x.shape[-1]
+        up = self._new(n, 2 * h, 2 * w, c)
+        ops.upsample2x(x, up)
+        out = self._new(n, 2 * h, 2 * w, c)
+        ops.gemm([Src.nhwc(up)], taps3x3(0, c), (2 * w, 2 * h, n), wb[0], out, bias=wb[1])
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states, image_hidden_states=None, kv_map=None):
+        dev = self.dev
+        n, _, h, w = sample.shape
+        if (h % (1 << self.model.num_upsamplers)) or (w % (1 << self.model.num_upsamplers)):
+            raise NotImplementedError("latent height/width must be divisible by 2**num_upsamplers")
+        sample = sample.to(dev, F32).contiguous()
+        if torch.is_tensor(timestep):
+            t = timestep.to(dev, F32).reshape(-1)
+            t = t.expand(n).contiguous() if t.numel() == 1 else t.contiguous()
+        else:
+            t = torch.full((n,), float(timestep), device=dev, dtype=F32)
+        if t.numel() != n:
+            raise ValueError(f"timestep has {t.numel()} entries for a batch of {n}")
+        text3 = encoder_hidden_states.to(dev, BF16).contiguous()
+        if text3.shape[0] != n or text3.shape[2] != self.model.config.cross_attention_dim:
+            raise ValueError(f"encoder_hidden_states {tuple(text3.shape)} does not match batch {n} / "
+                             f"cross_attention_dim {self.model.config.cross_attention_dim}")
+        L = text3.shape[1]
+        text = text3.view(n * L, -1)
+        img = None
+        if image_hidden_states is not None:
+            img = {k: v.to(dev, BF16).contiguous() for k, v in image_hidden_states.items()}
+        if kv_map is not None:
+            kv_map = kv_map.to(dev, torch.int32).contiguous()
+        need = ops._lib.load().sg_groupnorm_ws_floats(n, self.groups)
+        if self._stats is None or self._stats.numel() < need:
+            self._stats = torch.empty(need, dtype=F32, device=dev)
+
+        # time embedding: features -> linear_1 -> SiLU -> linear_2, then all 22 time_emb_proj at once
+        boc0 = self.boc[0]
+        tf = ops.timestep_features(t, boc0, self._new(n, boc0, dtype=F32))
+        e1 = ops.small_linear(tf, self.time[0], self.time[1], self._new(n, self.temb_dim, dtype=F32), silu_out=True)
+        emb = ops.small_linear(e1, self.time[2], self.time[3], self._new(n, self.temb_dim, dtype=F32))
+        lane_bias = ops.small_linear(emb, self.temb_w, self.temb_b, self._new(n, self.temb_w.shape[0], dtype=F32),
+                                     silu_in=True)
+
+        taps: Dict[str, torch.Tensor] = {}
+
+        def attn(p, x, hh, ww, key):
+            image = None
+            if img is not None:
+                if key not in img:
+                    raise KeyError(f"image_hidden_states is missing key {key!r}")
+                image = img[key]
+                if image.shape[2] != p["c"] or image.shape[1] % (hh * ww):
+                    raise ValueError(f"image_hidden_states[{key!r}] has shape {tuple(image.shape)}; expected "
+                                     f"(lanes, R*{hh * ww}, {p['c']})")
+                if kv_map is None and image.shape[0] != n:
+                    raise ValueError(f"image_hidden_states[{key!r}] has {image.shape[0]} lanes for a batch of {n}")
+            out, tap = self._transformer(p, x, n, hh, ww, text, L, image, kv_map, 0)
+            if img is None:
+                taps[key] = tap
+            return out
+
+        x = ops.conv_in(sample, self.conv_in[0], self.conv_in[1], self._new(n, h, w, boc0))
+        skips = [x]
+        hh, ww = h, w
+        for i, blk in enumerate(self.down):
+            for j, rp in enumerate(blk["res"]):
+                x = self._resnet(rp, x, None, n, hh, ww, lane_bias)
+                if blk["attn"] is not None:
+                    x = attn(blk["attn"][j], x, hh, ww, f"down_{i + 1}_{j + 1}")
+                skips.append(x)
+            if blk["down"] is not None:
+                x = self._downsample(blk["down"], x, n, hh, ww)
+                hh, ww = hh // 2, ww // 2
+                skips.append(x)
+        x = self._resnet(self.mid["res"][0], x, None, n, hh, ww, lane_bias)
+        x = attn(self.mid["attn"][0], x, hh, ww, "mid")
+        x = self._resnet(self.mid["res"][1], x, None, n, hh, ww, lane_bias)
+        for i, blk in enumerate(self.up):
+            for j, rp in enumerate(blk["res"]):
+                x = self._resnet(rp, x, skips.pop(), n, hh, ww, lane_bias)
+                if blk["attn"] is not None:
+                    x = attn(blk["attn"][j], x, hh, ww, f"up_{i}_{j + 1}")
+            if blk["up"] is not None:
+                x = self._upsample(blk["up"], x, n, hh, ww)
+                hh, ww = hh * 2, ww * 2
+        xn = self._gn(x.view(n, hh * ww, -1), None, n, hh * ww, self.norm_out, self.eps, True)
+        out = ops.conv_out(xn.view(n, hh, ww, -1), self.conv_out[0], self.conv_out[1],
+                           self._new(n, self.conv_out[0].shape[0], hh, ww, dtype=F32))
+        return out, taps

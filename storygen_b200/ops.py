@@ -1,0 +1,210 @@
+"""Torch-tensor front end of the C ABI: every function checks device/dtype/contiguity, builds the
+argument struct and enqueues ONE kernel on torch's current CUDA stream.  PyTorch is used only for
+device memory and streams; none of these functions has a torch / CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import SG_EPI_GEGLU, SG_EPI_LINEAR, SgAttnArgs, SgGemmArgs
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the StoryGen hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+
+
+class Src:
+    """One NHWC activation source of the implicit-GEMM A operand: (ptr, dims, strides) in elements."""
+
+    __slots__ = ("t", "ptr", "c", "w", "h", "n", "sw", "sh", "sn")
+
+    def __init__(self, t: torch.Tensor, c: int, w: int, h: int, n: int, sw: int, sh: int, sn: int, offset: int = 0):
+        self.t = t  # keeps the storage alive
+        self.ptr = t.data_ptr() + 2 * offset
+        self.c, self.w, self.h, self.n, self.sw, self.sh, self.sn = c, w, h, n, sw, sh, sn
+
+    @staticmethod
+    def rows(t: torch.Tensor) -> "Src":
+        """(M, K) row-major matrix as a 1 x 1 x M 'image' with K channels."""
+        m, k = t.shape
+        return Src(t, k, m, 1, 1, k, m * k, m * k)
+
+    @staticmethod
+    def nhwc(t: torch.Tensor) -> "Src":
+        n, h, w, c = t.shape
+        return Src(t, c, w, h, n, c, w * c, h * w * c)
+
+    @staticmethod
+    def nhwc_phase(t: torch.Tensor, py: int, px: int) -> "Src":
+        """Every second pixel starting at (py, px): the 4 phases turn a stride-2 conv into stride-1 taps."""
+        n, h, w, c = t.shape
+        return Src(t, c, w // 2, h // 2, n, 2 * c, 2 * w * c, h * w * c, offset=(py * w + px) * c)
+
+
+def tile_box(w: int, h: int, n: int) -> Tuple[int, int, int]:
+    """128-row tile as a bw x bh x bn box of the output pixel grid."""
+    bw = math.gcd(w, 128)
+    bh = math.gcd(h, 128 // bw)
+    return bw, bh, 128 // (bw * bh)
+
+
+def gemm(srcs: Sequence[Src], segs: Sequence[Tuple[int, int, int, int, int]], grid: Tuple[int, int, int],
+         weight: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None,
+         lane_bias: Optional[torch.Tensor] = None, ld_lane_bias: int = 0, residual: Optional[torch.Tensor] = None,
+         res_scale: float = 1.0, mode: int = SG_EPI_LINEAR) -> torch.Tensor:
+    """out[m, :] = epilogue(sum_k A[m, k] W[:, k]); see include/storygen_b200.h (sg_gemm).
+    segs: (src, dx, dy, c0, nkb); grid: (out_w, out_h, out_n); weight: bf16 [N, Ktot]."""
+    a = SgGemmArgs()
+    a.num_src = len(srcs)
+    for i, s in enumerate(srcs):
+        e = a.src[i]
+        e.ptr, e.dim_c, e.dim_w, e.dim_h, e.dim_n = s.ptr, s.c, s.w, s.h, s.n
+        e.stride_w, e.stride_h, e.stride_n = s.sw, s.sh, s.sn
+    a.num_segs = len(segs)
+    for i, (src, dx, dy, c0, nkb) in enumerate(segs):
+        e = a.segs[i]
+        e.src, e.dx, e.dy, e.c0, e.nkb = src, dx, dy, c0, nkb
+    a.out_w, a.out_h, a.out_n = grid
+    a.bw, a.bh, a.bn = tile_box(*grid)
+    _req(weight, BF16, "weight")
+    _req(out, BF16, "out")
+    a.b = weight.data_ptr()
+    a.N, a.Ktot = weight.shape
+    a.mode = mode
+    a.res_scale = res_scale
+    a.bias = _ptr(bias)
+    a.lane_bias = _ptr(lane_bias)
+    a.ld_lane_bias = ld_lane_bias
+    a.residual = _ptr(residual)
+    a.ldr = residual.shape[-1] if residual is not None else 0
+    a.out = out.data_ptr()
+    a.ldo = out.shape[-1]
+    _lib.check(_lib.load().sg_gemm(C.byref(a), _stream()), "sg_gemm")
+    return out
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, bias=None, residual=None, res_scale=1.0,
+           mode=SG_EPI_LINEAR) -> torch.Tensor:
+    """x (M, K) bf16 @ weight (N, K)^T with the fused epilogue."""
+    m, k = x.shape
+    return gemm([Src.rows(x)], [(0, 0, 0, 0, k // 64)], (m, 1, 1), weight, out, bias=bias, residual=residual,
+                res_scale=res_scale, mode=mode)
+
+
+def taps3x3(src: int, cin: int, c0: int = 0) -> List[Tuple[int, int, int, int, int]]:
+    return [(src, kx - 1, ky - 1, c0, cin // 64) for ky in range(3) for kx in range(3)]
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, n_lanes: int, n_heads: int,
+              head_dim: int, nq: int, nk: int, q_strides: Tuple[int, int], k_strides: Tuple[int, int],
+              v_strides: Tuple[int, int], n_kv_lanes: int = 0, kv_map: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(Q K^T / sqrt(d)) V per (lane, head); q/k/v may be strided views into fused projections.
+    *_strides = (lane stride, token stride) in elements."""
+    a = SgAttnArgs()
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.q_stride_n, a.q_stride_t = q_strides
+    a.k_stride_n, a.k_stride_t = k_strides
+    a.v_stride_n, a.v_stride_t = v_strides
+    c = n_heads * head_dim
+    a.o_stride_n, a.o_stride_t = nq * c, c
+    a.n_lanes, a.n_heads, a.head_dim, a.nq, a.nk = n_lanes, n_heads, head_dim, nq, nk
+    a.n_kv_lanes = n_kv_lanes
+    a.kv_map = _ptr(kv_map)
+    a.scale = head_dim ** -0.5
+    _lib.check(_lib.load().sg_attention(C.byref(a), _stream()), "sg_attention")
+    return out
+
+
+def groupnorm(x0: torch.Tensor, x1: Optional[torch.Tensor], n: int, hw: int, groups: int, eps: float,
+              gamma: torch.Tensor, beta: torch.Tensor, silu: bool, out: torch.Tensor, stats: torch.Tensor):
+    """y = [SiLU](GroupNorm(concat_c(x0, x1))); x* are (n, hw, c*) bf16.  Two launches (stats, apply)."""
+    lib = _lib.load()
+    c0 = x0.shape[-1]
+    c1 = x1.shape[-1] if x1 is not None else 0
+    _lib.check(lib.sg_groupnorm_stats(x0.data_ptr(), c0, _ptr(x1), c1, n, hw, groups, eps, stats.data_ptr(),
+                                      _stream()), "sg_groupnorm_stats")
+    _lib.check(lib.sg_groupnorm_apply(x0.data_ptr(), c0, _ptr(x1), c1, n, hw, groups, eps, stats.data_ptr(),
+                                      gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(), _stream()),
+               "sg_groupnorm_apply")
+    return out
+
+
+def groupnorm_ws(n: int, groups: int, device) -> torch.Tensor:
+    return torch.empty(_lib.load().sg_groupnorm_ws_floats(n, groups), dtype=torch.float32, device=device)
+
+
+def layernorm(x: torch.Tensor, eps: float, ga, ba, ya, gb=None, bb=None, yb=None):
+    rows, c = x.shape
+    _lib.check(_lib.load().sg_layernorm(x.data_ptr(), rows, c, eps, ga.data_ptr(), ba.data_ptr(), ya.data_ptr(),
+                                        _ptr(gb), _ptr(bb), _ptr(yb), _stream()), "sg_layernorm")
+
+
+def timestep_features(t: torch.Tensor, dim: int, out: torch.Tensor):
+    _req(t, torch.float32, "timesteps")
+    _lib.check(_lib.load().sg_timestep_features(t.data_ptr(), t.numel(), dim, out.data_ptr(), _stream()),
+               "sg_timestep_features")
+    return out
+
+
+def small_linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out: torch.Tensor, silu_in=False,
+                 silu_out=False):
+    n, k = x.shape
+    _lib.check(_lib.load().sg_small_linear(x.data_ptr(), n, k, w.data_ptr(), _ptr(b), w.shape[0], int(silu_in),
+                                           int(silu_out), out.data_ptr(), _stream()), "sg_small_linear")
+    return out
+
+
+def upsample2x(x: torch.Tensor, out: torch.Tensor):
+    n, h, w, c = x.shape
+    _lib.check(_lib.load().sg_upsample2x(x.data_ptr(), n, h, w, c, out.data_ptr(), _stream()), "sg_upsample2x")
+    return out
+
+
+def conv_in(x_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out_nhwc: torch.Tensor):
+    _req(x_nchw, torch.float32, "sample")
+    n, cin, h, ww = x_nchw.shape
+    _lib.check(_lib.load().sg_conv_in(x_nchw.data_ptr(), n, cin, h, ww, w.data_ptr(), b.data_ptr(), w.shape[0],
+                                      out_nhwc.data_ptr(), _stream()), "sg_conv_in")
+    return out_nhwc
+
+
+def conv_out(x_nhwc: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out_nchw: torch.Tensor):
+    n, h, ww, cin = x_nhwc.shape
+    _lib.check(_lib.load().sg_conv_out(x_nhwc.data_ptr(), n, cin, h, ww, w.data_ptr(), b.data_ptr(), w.shape[0],
+                                       out_nchw.data_ptr(), _stream()), "sg_conv_out")
+    return out_nchw
+
+
+def add_noise(x: torch.Tensor, eps: torch.Tensor, acp: torch.Tensor, t: torch.Tensor, out: torch.Tensor):
+    """out[n] = sqrt(acp[t[n]]) x[n] + sqrt(1 - acp[t[n]]) eps[n]; fp32, t int32 (device)."""
+    n = x.shape[0]
+    _lib.check(_lib.load().sg_add_noise(x.data_ptr(), eps.data_ptr(), acp.data_ptr(), t.data_ptr(), n,
+                                        x.numel() // n, out.data_ptr(), _stream()), "sg_add_noise")
+    return out
+
+
+def cfg_ddim_step(eps3: torch.Tensor, latents: torch.Tensor, s_img: float, s_txt: float, alphas: torch.Tensor):
+    """In-place dual-guidance DDIM update of `latents` (b, ...) from eps3 (3b, ...); alphas = device (a_t, a_prev)."""
+    b = latents.shape[0]
+    _lib.check(_lib.load().sg_cfg_ddim_step(eps3.data_ptr(), latents.data_ptr(), b, latents.numel() // b, s_img,
+                                            s_txt, alphas.data_ptr(), _stream()), "sg_cfg_ddim_step")
+    return latents

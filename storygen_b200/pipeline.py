@@ -1,0 +1,255 @@
+"""StableDiffusionPipeline with the reference's interface (model/pipeline.py:22-491) whose denoising
+loop — R feature passes + 1 denoise pass per step, dual-scale classifier-free guidance, eta=0 DDIM
+update (model/pipeline.py:411-469) — runs on the sm_100a kernels.
+
+Restructuring relative to the reference (results unchanged):
+  * the R feature passes of a step are ONE UNet call over R*2B lanes with a per-lane timestep vector,
+    lanes ordered (guidance lane, image, frame) so the 16 tapped feature maps land directly in the
+    (lanes, R*HW, C) layout the image cross-attention reads — the reference's torch.cat over frames
+    (model/pipeline.py:441-443) never happens;
+  * the reference's third feature-pass CFG lane duplicates the second (model/pipeline.py:429-430);
+    it is not recomputed: denoise-pass lanes [image] and [text+image] share one K/V lane (kv_map);
+  * a whole denoising step is captured once into a CUDA graph and replayed for the remaining steps.
+Tokenizer / CLIP / VAE are the caller's torch modules and run either side of the hot path unchanged.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from .scheduler import DDIMScheduler
+
+F32 = torch.float32
+
+
+@dataclass
+class StableDiffusionPipelineOutput:
+    images: object
+    nsfw_content_detected: Optional[List[bool]] = None
+
+
+def feature_timesteps(t: int, num_frames: int, stage: str) -> List[int]:
+    """model/pipeline.py:414-427: ref_t = long(t / 10); 'auto-regressive' noises the oldest frame most."""
+    ref_t = int(t / 10)
+    if stage == "auto-regressive":
+        return [ref_t * (num_frames - i) for i in range(num_frames)]
+    if stage == "multi-image-condition":
+        return [ref_t] * num_frames
+    raise NotImplementedError(f"stage {stage!r}: only 'auto-regressive' and 'multi-image-condition' condition the "
+                              "UNet on prior frames (model/pipeline.py:419-436)")
+
+
+class _DenoiseLoop:
+    """Static buffers + (optionally) one captured CUDA graph of a full denoising step."""
+
+    def __init__(self, unet, scheduler: DDIMScheduler, latents, text_uncond, text_cond, prev_uncond, prev_cond,
+                 frame_latents, zero_latents, noise, num_inference_steps, guidance_scale, image_guidance_scale, stage):
+        dev = unet.device
+        self.unet, self.eng = unet, unet.engine()
+        B, R = latents.shape[0], len(frame_latents)
+        self.B, self.R = B, R
+        self.s_txt, self.s_img = float(guidance_scale), float(image_guidance_scale)
+        f = lambda x: x.to(dev, F32).contiguous()
+        self.latents = f(latents).clone()
+        scheduler.set_timesteps(num_inference_steps, device="cpu")
+        self.timesteps = [int(t) for t in scheduler.timesteps]
+        # feature-pass lanes: index ((g * B + b) * R + r), g = 0 "no image" lane (zero frame), g = 1 frame lane
+        nf = 2 * B * R
+        src = torch.empty(2, B, R, *latents.shape[1:], dtype=F32, device=dev)
+        eps = torch.empty_like(src)
+        txt = torch.empty(2, B, R, *text_cond.shape[1:], dtype=torch.bfloat16, device=dev)
+        for r in range(R):
+            src[0, :, r] = f(zero_latents)
+            src[1, :, r] = f(frame_latents[r])
+            eps[:, :, r] = f(noise)[None]
+            txt[0, :, r] = prev_uncond[r].to(dev, torch.bfloat16)
+            txt[1, :, r] = prev_cond[r].to(dev, torch.bfloat16)
+        self.f_src, self.f_eps = src.view(nf, *latents.shape[1:]), eps.view(nf, *latents.shape[1:])
+        self.f_text = txt.view(nf, *text_cond.shape[1:])
+        self.f_noisy = torch.empty_like(self.f_src)
+        self.m_text = torch.cat([text_uncond, text_uncond, text_cond]).to(dev, torch.bfloat16).contiguous()
+        self.lat3 = torch.empty(3 * B, *latents.shape[1:], dtype=F32, device=dev)
+        # denoise lane (g3, b): g3 = 0 -> K/V lane b (zero frame); g3 = 1, 2 -> K/V lane B + b
+        self.kv_map = torch.tensor([b for b in range(B)] + [B + b for b in range(B)] * 2, dtype=torch.int32, device=dev)
+        self.acp = scheduler.alphas_cumprod.to(dev, F32).contiguous()
+        # per-step scalars, resident on the device: [f_t (nf) | m_t (3B) | a_t, a_prev] and int32 f_t
+        S = len(self.timesteps)
+        tab = torch.empty(S, nf + 3 * B + 2, dtype=F32)
+        tab_i = torch.empty(S, nf, dtype=torch.int32)
+        for s, t in enumerate(self.timesteps):
+            ft = torch.tensor(feature_timesteps(t, R, stage), dtype=F32).repeat(2 * B)
+            tab[s, :nf] = ft
+            tab_i[s] = ft.to(torch.int32)
+            tab[s, nf:nf + 3 * B] = float(t)
+            a_t, a_prev = scheduler.step_alphas(t)
+            tab[s, nf + 3 * B], tab[s, nf + 3 * B + 1] = a_t, a_prev
+        self.tab, self.tab_i = tab.to(dev), tab_i.to(dev)
+        self.par = torch.empty(nf + 3 * B + 2, dtype=F32, device=dev)
+        self.par_i = torch.empty(nf, dtype=torch.int32, device=dev)
+        self.nf = nf
+        self.graph = None
+
+    def _step_body(self):
+        nf, B = self.nf, self.B
+        ops.add_noise(self.f_src, self.f_eps, self.acp, self.par_i, self.f_noisy)
+        taps = self.eng.forward(self.f_noisy, self.par[:nf], self.f_text, None)[1]
+        cond = {k: v.view(2 * B, -1, v.shape[-1]) for k, v in taps.items()}
+        self.lat3.view(3, B, -1).copy_(self.latents.view(1, B, -1).expand(3, B, -1))
+        eps3 = self.eng.forward(self.lat3, self.par[nf:nf + 3 * B], self.m_text, cond, kv_map=self.kv_map)[0]
+        ops.cfg_ddim_step(eps3, self.latents, self.s_img, self.s_txt, self.par[nf + 3 * B:])
+
+    def run(self, use_cuda_graph: bool = True, callback=None, callback_steps: int = 1):
+        for s, t in enumerate(self.timesteps):
+            self.par.copy_(self.tab[s])
+            self.par_i.copy_(self.tab_i[s])
+            if not use_cuda_graph:
+                self._step_body()
+            elif self.graph is None:
+                if s == 0:
+                    self._step_body()  # eager first step doubles as warm-up (module attributes, allocator)
+                else:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._step_body()
+                    self.graph = g
+                    g.replay()
+            else:
+                self.graph.replay()
+            if callback is not None and s % callback_steps == 0:
+                callback(s, t, self.latents)
+        return self.latents
+
+
+class StableDiffusionPipeline:
+    """Same constructor and __call__ as the reference's model/pipeline.py::StableDiffusionPipeline."""
+
+    def __init__(self, vae, text_encoder, tokenizer, unet, scheduler):
+        self.vae, self.text_encoder, self.tokenizer, self.unet, self.scheduler = vae, text_encoder, tokenizer, unet, scheduler
+        boc = getattr(getattr(vae, "config", None), "block_out_channels", (128, 256, 512, 512))
+        self.vae_scale_factor = 2 ** (len(boc) - 1)
+        self._progress_bar_config: Dict = {}
+        self.use_cuda_graph = True
+
+    # ---- diffusers.DiffusionPipeline plumbing the reference's callers touch ----------------------
+    @property
+    def device(self):
+        return self.unet.device
+
+    _execution_device = device
+
+    def set_progress_bar_config(self, **kwargs):
+        self._progress_bar_config = kwargs
+
+    def enable_xformers_memory_efficient_attention(self, *a, **k):
+        return None  # the fused tcgen05 attention kernel is always on
+
+    def enable_vae_slicing(self):
+        return None
+
+    @staticmethod
+    def numpy_to_pil(images):
+        from PIL import Image
+        if images.ndim == 3:
+            images = images[None, ...]
+        images = (images * 255).round().astype("uint8")
+        return [Image.fromarray(image) for image in images]
+
+    # ---- text / image conditioning (the steps either side of the hot path; caller's modules) -----
+    def _encode_prompt(self, prompt, device, num_images_per_prompt, do_classifier_free_guidance, negative_prompt):
+        """model/pipeline.py:87-196 -> (2B or B, L, D): [uncond; cond]."""
+        batch_size = len(prompt) if isinstance(prompt, list) else 1
+        tok = self.tokenizer(prompt, padding="max_length", max_length=self.tokenizer.model_max_length, truncation=True,
+                             return_tensors="pt")
+        emb = self.text_encoder(tok.input_ids.to(device), attention_mask=None)[0]
+        bs, seq, _ = emb.shape
+        emb = emb.repeat(1, num_images_per_prompt, 1).view(bs * num_images_per_prompt, seq, -1)
+        if do_classifier_free_guidance:
+            if negative_prompt is None:
+                uncond_tokens = [""] * batch_size
+            elif isinstance(negative_prompt, str):
+                uncond_tokens = [negative_prompt]
+            else:
+                uncond_tokens = negative_prompt
+            utok = self.tokenizer(uncond_tokens, padding="max_length", max_length=tok.input_ids.shape[-1],
+                                  truncation=True, return_tensors="pt")
+            un = self.text_encoder(utok.input_ids.to(device), attention_mask=None)[0]
+            un = un.repeat(1, num_images_per_prompt, 1).view(batch_size * num_images_per_prompt, un.shape[1], -1)
+            emb = torch.cat([un, emb])
+        return emb
+
+    def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
+        shape = (batch_size, num_channels_latents, height // self.vae_scale_factor, width // self.vae_scale_factor)
+        if latents is None:
+            if isinstance(generator, list):
+                latents = torch.cat([torch.randn((1,) + shape[1:], generator=generator[i], device=device, dtype=dtype)
+                                     for i in range(batch_size)], dim=0)
+            else:
+                latents = torch.randn(shape, generator=generator, device=device, dtype=dtype)
+        elif latents.shape != shape:
+            raise ValueError(f"Unexpected inputs shape, got {latents.shape}, expected {shape}")
+        return latents.to(device) * self.scheduler.init_noise_sigma
+
+    def decode_latents(self, latents):
+        image = self.vae.decode((1 / 0.18215 * latents).to(next(self.vae.parameters()).dtype)).sample
+        image = (image / 2 + 0.5).clamp(0, 1)
+        return image.permute(0, 2, 3, 1).cpu().float().numpy()
+
+    # ---- the hot path on synthetic / pre-encoded inputs ------------------------------------------
+    @torch.no_grad()
+    def denoise(self, latents, text_uncond, text_cond, prev_uncond: Sequence[torch.Tensor],
+                prev_cond: Sequence[torch.Tensor], frame_latents: Sequence[torch.Tensor], zero_latents, noise,
+                num_inference_steps: int = 50, guidance_scale: float = 7.0, image_guidance_scale: float = 3.5,
+                stage: str = "auto-regressive", callback=None, callback_steps: int = 1) -> torch.Tensor:
+        """Denoise B latents conditioned on R prior frames; every argument is a tensor (or list of R
+        tensors) with leading dimension B.  Returns fp32 latents (B, 4, h, w) on the UNet's device."""
+        if guidance_scale <= 1.0:
+            raise NotImplementedError("guidance_scale <= 1 is broken in the reference (model/pipeline.py:430); "
+                                      "only the classifier-free-guidance path is implemented")
+        loop = _DenoiseLoop(self.unet, self.scheduler, latents, text_uncond, text_cond, prev_uncond, prev_cond,
+                            frame_latents, zero_latents, noise, num_inference_steps, guidance_scale,
+                            image_guidance_scale, stage)
+        return loop.run(self.use_cuda_graph, callback, callback_steps)
+
+    # ---- reference-compatible entry point ---------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, stage, prompt: Union[str, List[str]], image_prompt=None, prev_prompt=None,
+                 height: Optional[int] = None, width: Optional[int] = None, num_inference_steps: int = 50,
+                 guidance_scale: float = 7.5, image_guidance_scale: float = 3.5, negative_prompt=None,
+                 num_images_per_prompt: Optional[int] = 1, eta: float = 0.0, generator=None, latents=None,
+                 output_type: Optional[str] = "pil", return_dict: bool = True, callback: Optional[Callable] = None,
+                 callback_steps: Optional[int] = 1):
+        """model/pipeline.py:273-484.  The global-RNG draws happen in the reference's order: VAE posterior
+        of the zero image, of each prior frame, then one `noise` tensor shared by all frames and steps."""
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        if height % 8 or width % 8:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if eta != 0.0:
+            raise NotImplementedError("eta != 0")
+        batch_size = 1 if isinstance(prompt, str) else len(prompt)
+        device = self._execution_device
+        nipp = num_images_per_prompt
+        te = self._encode_prompt(prompt, device, nipp, True, negative_prompt)
+        prev = [self._encode_prompt(p, device, nipp, True, negative_prompt) for p in prev_prompt]
+        B = batch_size * nipp
+        latents = self.prepare_latents(B, self.unet.in_channels, height, width, te.dtype, device, generator, latents)
+        vae_dtype = next(self.vae.parameters()).dtype
+        image_prompt = image_prompt.to(device=device, dtype=vae_dtype)
+        frames = torch.transpose(image_prompt, 0, 1)
+        zero = self.vae.encode(frames[0] * 0).latent_dist.sample() * 0.18215
+        zero = zero.repeat(nipp, 1, 1, 1)
+        frame_latents = [(self.vae.encode(fr).latent_dist.sample() * 0.18215).repeat(nipp, 1, 1, 1) for fr in frames]
+        noise = torch.randn_like(frame_latents[0])
+        out = self.denoise(latents, te[:B], te[B:], [p[:B] for p in prev], [p[B:] for p in prev], frame_latents, zero,
+                           noise, num_inference_steps, guidance_scale, image_guidance_scale, stage, callback,
+                           callback_steps or 1)
+        image = self.decode_latents(out)
+        if output_type == "pil":
+            image = self.numpy_to_pil(image)
+        if not return_dict:
+            return (image, None)
+        return StableDiffusionPipelineOutput(images=image, nsfw_content_detected=None)
