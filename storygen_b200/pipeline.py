@@ -44,35 +44,28 @@ def feature_timesteps(t: int, num_frames: int, stage: str) -> List[int]:
 
 
 class _DenoiseLoop:
-    """Static buffers + (optionally) one captured CUDA graph of a full denoising step."""
+    """Static device buffers for one (B, R, latent shape, text shape, #steps, stage) configuration and one
+    captured CUDA graph of a full denoising step; `load()` refills the buffers so the graph is reused
+    across calls."""
 
-    def __init__(self, unet, scheduler: DDIMScheduler, latents, text_uncond, text_cond, prev_uncond, prev_cond,
-                 frame_latents, zero_latents, noise, num_inference_steps, guidance_scale, image_guidance_scale, stage):
+    def __init__(self, unet, scheduler: DDIMScheduler, B, R, lat_shape, text_shape, num_inference_steps,
+                 guidance_scale, image_guidance_scale, stage):
         dev = unet.device
         self.unet, self.eng = unet, unet.engine()
-        B, R = latents.shape[0], len(frame_latents)
         self.B, self.R = B, R
         self.s_txt, self.s_img = float(guidance_scale), float(image_guidance_scale)
-        f = lambda x: x.to(dev, F32).contiguous()
-        self.latents = f(latents).clone()
         scheduler.set_timesteps(num_inference_steps, device="cpu")
         self.timesteps = [int(t) for t in scheduler.timesteps]
         # feature-pass lanes: index ((g * B + b) * R + r), g = 0 "no image" lane (zero frame), g = 1 frame lane
         nf = 2 * B * R
-        src = torch.empty(2, B, R, *latents.shape[1:], dtype=F32, device=dev)
-        eps = torch.empty_like(src)
-        txt = torch.empty(2, B, R, *text_cond.shape[1:], dtype=torch.bfloat16, device=dev)
-        for r in range(R):
-            src[0, :, r] = f(zero_latents)
-            src[1, :, r] = f(frame_latents[r])
-            eps[:, :, r] = f(noise)[None]
-            txt[0, :, r] = prev_uncond[r].to(dev, torch.bfloat16)
-            txt[1, :, r] = prev_cond[r].to(dev, torch.bfloat16)
-        self.f_src, self.f_eps = src.view(nf, *latents.shape[1:]), eps.view(nf, *latents.shape[1:])
-        self.f_text = txt.view(nf, *text_cond.shape[1:])
-        self.f_noisy = torch.empty_like(self.f_src)
-        self.m_text = torch.cat([text_uncond, text_uncond, text_cond]).to(dev, torch.bfloat16).contiguous()
-        self.lat3 = torch.empty(3 * B, *latents.shape[1:], dtype=F32, device=dev)
+        self.nf = nf
+        self.latents = torch.empty(B, *lat_shape, dtype=F32, device=dev)
+        self.f_src = torch.empty(2, B, R, *lat_shape, dtype=F32, device=dev)
+        self.f_eps = torch.empty_like(self.f_src)
+        self.f_text = torch.empty(2, B, R, *text_shape, dtype=torch.bfloat16, device=dev)
+        self.f_noisy = torch.empty(nf, *lat_shape, dtype=F32, device=dev)
+        self.m_text = torch.empty(3, B, *text_shape, dtype=torch.bfloat16, device=dev)
+        self.lat3 = torch.empty(3 * B, *lat_shape, dtype=F32, device=dev)
         # denoise lane (g3, b): g3 = 0 -> K/V lane b (zero frame); g3 = 1, 2 -> K/V lane B + b
         self.kv_map = torch.tensor([b for b in range(B)] + [B + b for b in range(B)] * 2, dtype=torch.int32, device=dev)
         self.acp = scheduler.alphas_cumprod.to(dev, F32).contiguous()
@@ -90,35 +83,57 @@ class _DenoiseLoop:
         self.tab, self.tab_i = tab.to(dev), tab_i.to(dev)
         self.par = torch.empty(nf + 3 * B + 2, dtype=F32, device=dev)
         self.par_i = torch.empty(nf, dtype=torch.int32, device=dev)
-        self.nf = nf
         self.graph = None
+        self.kernels_per_step = 0
+        self.kernel_launches = 0
+
+    def load(self, latents, text_uncond, text_cond, prev_uncond, prev_cond, frame_latents, zero_latents, noise):
+        """Copy one batch of inputs (host or device tensors) into the static buffers."""
+        nb = dict(non_blocking=True)
+        self.latents.copy_(latents, **nb)
+        for r in range(self.R):
+            self.f_src[0, :, r].copy_(zero_latents, **nb)
+            self.f_src[1, :, r].copy_(frame_latents[r], **nb)
+            self.f_eps[0, :, r].copy_(noise, **nb)
+            self.f_eps[1, :, r].copy_(noise, **nb)
+            self.f_text[0, :, r].copy_(prev_uncond[r], **nb)
+            self.f_text[1, :, r].copy_(prev_cond[r], **nb)
+        self.m_text[0].copy_(text_uncond, **nb)
+        self.m_text[1].copy_(text_uncond, **nb)
+        self.m_text[2].copy_(text_cond, **nb)
 
     def _step_body(self):
         nf, B = self.nf, self.B
-        ops.add_noise(self.f_src, self.f_eps, self.acp, self.par_i, self.f_noisy)
-        taps = self.eng.forward(self.f_noisy, self.par[:nf], self.f_text, None)[1]
+        lat_shape = self.latents.shape[1:]
+        ops.add_noise(self.f_src.view(nf, *lat_shape), self.f_eps.view(nf, *lat_shape), self.acp, self.par_i, self.f_noisy)
+        taps = self.eng.forward(self.f_noisy, self.par[:nf], self.f_text.view(nf, *self.f_text.shape[3:]), None)[1]
         cond = {k: v.view(2 * B, -1, v.shape[-1]) for k, v in taps.items()}
         self.lat3.view(3, B, -1).copy_(self.latents.view(1, B, -1).expand(3, B, -1))
-        eps3 = self.eng.forward(self.lat3, self.par[nf:nf + 3 * B], self.m_text, cond, kv_map=self.kv_map)[0]
+        eps3 = self.eng.forward(self.lat3, self.par[nf:nf + 3 * B], self.m_text.view(3 * B, *self.m_text.shape[2:]), cond,
+                                kv_map=self.kv_map)[0]
         ops.cfg_ddim_step(eps3, self.latents, self.s_img, self.s_txt, self.par[nf + 3 * B:])
 
     def run(self, use_cuda_graph: bool = True, callback=None, callback_steps: int = 1):
+        from ._lib import launch_count
         for s, t in enumerate(self.timesteps):
             self.par.copy_(self.tab[s])
             self.par_i.copy_(self.tab_i[s])
-            if not use_cuda_graph:
-                self._step_body()
-            elif self.graph is None:
-                if s == 0:
-                    self._step_body()  # eager first step doubles as warm-up (module attributes, allocator)
-                else:
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
-                        self._step_body()
-                    self.graph = g
-                    g.replay()
-            else:
+            if self.graph is not None and use_cuda_graph:
                 self.graph.replay()
+                self.kernel_launches += self.kernels_per_step
+            elif not use_cuda_graph or self.kernels_per_step == 0:
+                # eager step (also the warm-up before capture: function attributes, allocator, tensor maps)
+                c0 = launch_count()
+                self._step_body()
+                self.kernels_per_step = launch_count() - c0
+                self.kernel_launches += self.kernels_per_step
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_body()
+                self.graph = g
+                g.replay()
+                self.kernel_launches += self.kernels_per_step
             if callback is not None and s % callback_steps == 0:
                 callback(s, t, self.latents)
         return self.latents
@@ -133,6 +148,8 @@ class StableDiffusionPipeline:
         self.vae_scale_factor = 2 ** (len(boc) - 1)
         self._progress_bar_config: Dict = {}
         self.use_cuda_graph = True
+        self._loops: Dict = {}
+        self.kernel_launches = 0  # native kernels enqueued by denoise() so far (graph replays included)
 
     # ---- diffusers.DiffusionPipeline plumbing the reference's callers touch ----------------------
     @property
@@ -209,10 +226,19 @@ class StableDiffusionPipeline:
         if guidance_scale <= 1.0:
             raise NotImplementedError("guidance_scale <= 1 is broken in the reference (model/pipeline.py:430); "
                                       "only the classifier-free-guidance path is implemented")
-        loop = _DenoiseLoop(self.unet, self.scheduler, latents, text_uncond, text_cond, prev_uncond, prev_cond,
-                            frame_latents, zero_latents, noise, num_inference_steps, guidance_scale,
-                            image_guidance_scale, stage)
-        return loop.run(self.use_cuda_graph, callback, callback_steps)
+        B, R = latents.shape[0], len(frame_latents)
+        key = (B, R, tuple(latents.shape[1:]), tuple(text_cond.shape[1:]), num_inference_steps, float(guidance_scale),
+               float(image_guidance_scale), stage, id(self.unet.engine()))
+        loop = self._loops.get(key)
+        if loop is None:
+            self._loops.clear()  # one resident configuration: its graph pool holds every activation buffer
+            loop = _DenoiseLoop(self.unet, self.scheduler, B, R, tuple(latents.shape[1:]), tuple(text_cond.shape[1:]),
+                                num_inference_steps, guidance_scale, image_guidance_scale, stage)
+            self._loops[key] = loop
+        loop.load(latents, text_uncond, text_cond, prev_uncond, prev_cond, frame_latents, zero_latents, noise)
+        out = loop.run(self.use_cuda_graph, callback, callback_steps)
+        self.kernel_launches = loop.kernel_launches
+        return out.clone()
 
     # ---- reference-compatible entry point ---------------------------------------------------------
     @torch.no_grad()

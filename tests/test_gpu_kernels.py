@@ -1,0 +1,197 @@
+"""GPU: every kernel through the C ABI (ctypes) against a plain fp32 torch restatement of the same op
+on identical bf16-rounded inputs.  Tolerances: bf16 output rounding (2^-8 relative) plus fp32
+accumulation-order noise; stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from storygen_b200 import _lib, ops
+from storygen_b200.ops import BF16, Src, taps3x3
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*shape, scale=1.0, seed=0, dtype=BF16):
+    g = torch.Generator("cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+def close(got, ref, rel=0.012, abs_=0.02):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs().max().item()
+    tol = abs_ + rel * ref.abs().max().item()
+    assert err <= tol, f"max err {err:.4g} > tol {tol:.4g} (ref max {ref.abs().max():.4g})"
+
+
+@pytest.mark.parametrize("m,k,n", [(128, 64, 64), (300, 320, 320), (4096, 640, 1280), (77 * 3, 768, 640), (1000, 1280, 960)])
+def test_linear_bias_residual(m, k, n):
+    x, w = rnd(m, k, seed=1), rnd(n, k, scale=k ** -0.5, seed=2)
+    b, r = rnd(n, seed=3, dtype=torch.float32), rnd(m, n, seed=4)
+    out = torch.empty(m, n, dtype=BF16, device=DEV)
+    ops.linear(x, w, out, bias=b, residual=r, res_scale=2.0)
+    close(out, x.float() @ w.float().T + b + 2.0 * r.float())
+
+
+def test_linear_geglu():
+    m, c = 512, 320
+    x, w, b = rnd(m, c, seed=1), rnd(8 * c, c, scale=c ** -0.5, seed=2), rnd(8 * c, seed=3, dtype=torch.float32)
+    half = 4 * c
+    wi = torch.stack([w[:half].reshape(-1, 16, c), w[half:].reshape(-1, 16, c)], 1).reshape(8 * c, c).contiguous()
+    bi = torch.stack([b[:half].reshape(-1, 16), b[half:].reshape(-1, 16)], 1).reshape(-1).contiguous()
+    out = torch.empty(m, half, dtype=BF16, device=DEV)
+    ops.linear(x, wi, out, bias=bi, mode=_lib.SG_EPI_GEGLU)
+    y = x.float() @ w.float().T + b
+    close(out, y[:, :half] * F.gelu(y[:, half:]))
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 64, 64, 64, 64), (3, 32, 32, 128, 320), (5, 8, 8, 256, 128), (1, 16, 16, 320, 640),
+                                            (1, 96, 96, 64, 64)])
+def test_conv3x3_time_embedding(n, h, w, cin, cout):
+    x = rnd(n, h, w, cin, seed=1)
+    wt = rnd(cout, cin, 3, 3, scale=(9 * cin) ** -0.5, seed=2, dtype=torch.float32)
+    temb = rnd(n, cout + 64, seed=3, dtype=torch.float32)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, -1).to(BF16).contiguous()
+    out = torch.empty(n, h, w, cout, dtype=BF16, device=DEV)
+    ops.gemm([Src.nhwc(x)], taps3x3(0, cin), (w, h, n), wp, out, lane_bias=temb[:, 64:], ld_lane_bias=temb.shape[1])
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wp.float().reshape(cout, 3, 3, cin).permute(0, 3, 1, 2), padding=1)
+    ref = ref + temb[:, 64:, None, None]
+    close(out, ref.permute(0, 2, 3, 1))
+
+
+def test_conv3x3_with_shortcut_over_concat():
+    n, h, w, c0, c1, cout = 2, 32, 32, 128, 64, 64
+    hn, x0, x1 = rnd(n, h, w, cout, seed=1), rnd(n, h, w, c0, seed=2), rnd(n, h, w, c1, seed=3)
+    w2 = rnd(cout, cout, 3, 3, scale=(9 * cout) ** -0.5, seed=4, dtype=torch.float32)
+    ws = rnd(cout, c0 + c1, scale=(c0 + c1) ** -0.5, seed=5, dtype=torch.float32)
+    b = rnd(cout, seed=6, dtype=torch.float32)
+    wp = torch.cat([w2.permute(0, 2, 3, 1).reshape(cout, -1), ws], 1).to(BF16).contiguous()
+    out = torch.empty(n, h, w, cout, dtype=BF16, device=DEV)
+    segs = taps3x3(0, cout) + [(1, 0, 0, 0, c0 // 64), (2, 0, 0, 0, c1 // 64)]
+    ops.gemm([Src.nhwc(hn), Src.nhwc(x0), Src.nhwc(x1)], segs, (w, h, n), wp, out, bias=b)
+    wq = wp.float()
+    ref = F.conv2d(hn.float().permute(0, 3, 1, 2), wq[:, :9 * cout].reshape(cout, 3, 3, cout).permute(0, 3, 1, 2), padding=1)
+    ref = ref + F.conv2d(torch.cat([x0, x1], -1).float().permute(0, 3, 1, 2), wq[:, 9 * cout:, None, None]) + b[None, :, None, None]
+    close(out, ref.permute(0, 2, 3, 1))
+
+
+def test_conv3x3_stride2():
+    n, h, w, c = 3, 32, 32, 128
+    x = rnd(n, h, w, c, seed=1)
+    wt = rnd(c, c, 3, 3, scale=(9 * c) ** -0.5, seed=2, dtype=torch.float32)
+    b = rnd(c, seed=3, dtype=torch.float32)
+    wp = wt.permute(0, 2, 3, 1).reshape(c, -1).to(BF16).contiguous()
+    out = torch.empty(n, h // 2, w // 2, c, dtype=BF16, device=DEV)
+    srcs = [Src.nhwc_phase(x, py, px) for py in range(2) for px in range(2)]
+    ph, sh = (1, 0, 1), (-1, 0, 0)
+    segs = [(ph[ky] * 2 + ph[kx], sh[kx], sh[ky], 0, c // 64) for ky in range(3) for kx in range(3)]
+    ops.gemm(srcs, segs, (w // 2, h // 2, n), wp, out, bias=b)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wp.float().reshape(c, 3, 3, c).permute(0, 3, 1, 2), bias=b, stride=2, padding=1)
+    close(out, ref.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("d,heads,n,nq,nk", [(40, 8, 2, 4096, 4096), (40, 8, 3, 1024, 77), (80, 8, 2, 1024, 3072), (160, 8, 2, 256, 768),
+                                             (160, 8, 3, 64, 192), (32, 2, 2, 512, 640), (64, 2, 1, 256, 256), (128, 2, 2, 64, 64)])
+def test_attention(d, heads, n, nq, nk):
+    c = heads * d
+    q, k, v = rnd(n, nq, c, seed=1), rnd(n, nk, c, seed=2), rnd(n, nk, c, seed=3)
+    out = torch.empty(n, nq, c, dtype=BF16, device=DEV)
+    ops.attention(q, k, v, out, n, heads, d, nq, nk, (nq * c, c), (nk * c, c), (nk * c, c))
+    sp = lambda t, L: t.float().view(n, L, heads, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp(q, nq), sp(k, nk), sp(v, nk)).transpose(1, 2).reshape(n, nq, c)
+    close(out, ref, rel=0.01, abs_=0.004)
+
+
+def test_attention_fused_qkv_kv_map_and_peaked_scores():
+    d, heads, nq = 40, 8, 512
+    c = heads * d
+    qkv = rnd(2, nq, 3 * c, scale=2.5, seed=5)  # large logits: exercises the lazy-rescale path
+    out = torch.empty(2, nq, c, dtype=BF16, device=DEV)
+    st = (nq * 3 * c, 3 * c)
+    ops.attention(qkv, qkv[..., c:], qkv[..., 2 * c:], out, 2, heads, d, nq, nq, st, st, st)
+    sp = lambda t: t.float().reshape(2, nq, heads, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp(qkv[..., :c]), sp(qkv[..., c:2 * c]), sp(qkv[..., 2 * c:])).transpose(1, 2).reshape(2, nq, c)
+    close(out, ref, rel=0.02, abs_=0.01)
+    # kv_map: three query lanes read K/V lanes (0, 1, 1)
+    q, k, v = rnd(3, 128, c, seed=6), rnd(2, 384, c, seed=7), rnd(2, 384, c, seed=8)
+    kv_map = torch.tensor([0, 1, 1], dtype=torch.int32, device=DEV)
+    out = torch.empty(3, 128, c, dtype=BF16, device=DEV)
+    ops.attention(q, k, v, out, 3, heads, d, 128, 384, (128 * c, c), (384 * c, c), (384 * c, c), n_kv_lanes=2, kv_map=kv_map)
+    idx = kv_map.long()
+    sp2 = lambda t, L: t.float().view(t.shape[0], L, heads, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp2(q, 128), sp2(k[idx], 384), sp2(v[idx], 384)).transpose(1, 2).reshape(3, 128, c)
+    close(out, ref, rel=0.01, abs_=0.004)
+
+
+@pytest.mark.parametrize("c0,c1,hw,groups,silu,eps", [(320, 0, 4096, 32, True, 1e-5), (1280, 640, 256, 32, True, 1e-5),
+                                                      (640, 320, 1024, 32, True, 1e-5), (1280, 1280, 64, 32, True, 1e-5),
+                                                      (64, 0, 4096, 8, False, 1e-6), (256, 128, 100, 8, True, 1e-5)])
+def test_groupnorm(c0, c1, hw, groups, silu, eps):
+    n = 3
+    x0 = rnd(n, hw, c0, seed=1) * 2 + 0.5
+    x1 = (rnd(n, hw, c1, seed=2) - 0.25) if c1 else None
+    c = c0 + c1
+    gamma, beta = rnd(c, seed=3, dtype=torch.float32) + 1, rnd(c, seed=4, dtype=torch.float32)
+    out = torch.empty(n, hw, c, dtype=BF16, device=DEV)
+    ops.groupnorm(x0, x1, n, hw, groups, eps, gamma, beta, silu, out, ops.groupnorm_ws(n, groups, DEV))
+    x = torch.cat([x0, x1], -1) if c1 else x0
+    ref = F.group_norm(x.float().transpose(1, 2), groups, gamma, beta, eps)
+    ref = F.silu(ref) if silu else ref
+    close(out, ref.transpose(1, 2), rel=0.01, abs_=0.01)
+
+
+@pytest.mark.parametrize("c", [64, 320, 640, 1280])
+def test_layernorm_two_outputs(c):
+    x = rnd(1000, c, seed=1) * 3 + 1
+    ga, ba, gb, bb = (rnd(c, seed=s, dtype=torch.float32) for s in (2, 3, 4, 5))
+    ya, yb = torch.empty_like(x), torch.empty_like(x)
+    ops.layernorm(x, 1e-5, ga, ba, ya, gb, bb, yb)
+    close(ya, F.layer_norm(x.float(), (c,), ga, ba, 1e-5), abs_=0.01)
+    close(yb, F.layer_norm(x.float(), (c,), gb, bb, 1e-5), abs_=0.01)
+    y1 = torch.empty_like(x)
+    ops.layernorm(x, 1e-5, ga, ba, y1)
+    assert torch.equal(y1, ya)
+
+
+def test_time_embedding_chain():
+    n, dim, temb = 5, 320, 1280
+    t = torch.tensor([0.0, 1.0, 98.0, 294.0, 981.0], device=DEV)
+    f = ops.timestep_features(t, dim, torch.empty(n, dim, device=DEV))
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, device=DEV, dtype=torch.float32) / half)
+    ref = torch.cat([torch.cos(t[:, None] * freqs), torch.sin(t[:, None] * freqs)], -1)
+    assert (f - ref).abs().max() < 2e-4  # fp32 sin/cos of arguments up to 981
+    w, b = rnd(temb, dim, scale=dim ** -0.5, seed=1), rnd(temb, seed=2, dtype=torch.float32)
+    y = ops.small_linear(f, w, b, torch.empty(n, temb, device=DEV), silu_in=True, silu_out=True)
+    close(y, F.silu(F.silu(f) @ w.float().T + b), rel=1e-3, abs_=1e-3)
+
+
+def test_upsample_conv_in_out_and_scheduler_kernels():
+    x = rnd(2, 8, 8, 64, seed=1)
+    up = ops.upsample2x(x, torch.empty(2, 16, 16, 64, dtype=BF16, device=DEV))
+    assert torch.equal(up, x.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    s = rnd(3, 4, 64, 64, seed=2, dtype=torch.float32)
+    w, b = rnd(320, 4, 3, 3, scale=1 / 6, seed=3, dtype=torch.float32), rnd(320, seed=4, dtype=torch.float32)
+    y = ops.conv_in(s, w, b, torch.empty(3, 64, 64, 320, dtype=BF16, device=DEV))
+    close(y, F.conv2d(s, w, b, padding=1).permute(0, 2, 3, 1), rel=0.005, abs_=0.005)
+    xo = rnd(3, 64, 64, 320, seed=5)
+    wo, bo = rnd(4, 320, 3, 3, scale=(9 * 320) ** -0.5, seed=6, dtype=torch.float32), rnd(4, seed=7, dtype=torch.float32)
+    yo = ops.conv_out(xo, wo, bo, torch.empty(3, 4, 64, 64, device=DEV))
+    close(yo, F.conv2d(xo.float().permute(0, 3, 1, 2), wo, bo, padding=1), rel=1e-3, abs_=1e-3)
+    # add_noise / cfg + ddim
+    acp = torch.linspace(0.999, 0.005, 1000, device=DEV)
+    lat, eps = rnd(4, 4, 64, 64, seed=8, dtype=torch.float32), rnd(4, 4, 64, 64, seed=9, dtype=torch.float32)
+    t = torch.tensor([0, 98, 294, 999], dtype=torch.int32, device=DEV)
+    out = ops.add_noise(lat, eps, acp, t, torch.empty_like(lat))
+    a = acp[t.long()].view(4, 1, 1, 1)
+    assert torch.allclose(out, a.sqrt() * lat + (1 - a).sqrt() * eps, atol=1e-6)
+    e3 = rnd(12, 4, 64, 64, seed=10, dtype=torch.float32)
+    l0 = lat.clone()
+    alphas = torch.tensor([0.3, 0.35], device=DEV)
+    ops.cfg_ddim_step(e3, lat, 3.5, 7.0, alphas)
+    u, i, al = e3.chunk(3)
+    e = u + 3.5 * (i - u) + 7.0 * (al - i)
+    x0 = (l0 - (1 - 0.3) ** 0.5 * e) / 0.3 ** 0.5
+    assert torch.allclose(lat, 0.35 ** 0.5 * x0 + (1 - 0.35) ** 0.5 * e, atol=1e-4, rtol=1e-5)

@@ -1,0 +1,148 @@
+"""GPU: the drop-in UNet / pipeline (C ABI underneath) against the fp32 oracle on identical seeded
+weights and inputs, and against the golden fixtures generated from the reference's own code.
+
+Tolerance (bf16 storage, fp32 accumulation, vs an fp32 oracle): max|delta| <= 0.10 * std(reference
+output).  Calibration: the reference's own torch code under bf16 autocast deviates from its fp32 run by
+5.9 % of the output std (sample) and 9.7 % (tapped features) — SURVEY.md §8c; this path measures
+4.4 % / 6.4 % (profiles/r01_unet_vs_oracle.log)."""
+import os
+
+import pytest
+import torch
+
+from conftest import GOLD
+from oracle import sampler
+from oracle.make_golden import cond_from_taps, sub, unet_inputs
+from oracle.unet import SD15_CONFIG, TINY_CONFIG, OracleUNet
+from oracle.weights import load_seeded
+from storygen_b200 import DDIMScheduler, StableDiffusionPipeline, UNet2DConditionModel, _lib
+
+pytestmark = pytest.mark.gpu
+REL = 0.10
+
+
+def build(cfg, seed=0):
+    ora = load_seeded(OracleUNet(**cfg).eval(), seed)
+    mod = UNet2DConditionModel(**cfg)
+    mod.load_state_dict(ora.state_dict())
+    return ora, mod.cuda().eval()
+
+
+def check(got, ref, rel=REL, what=""):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err, tol = (got - ref).abs().max().item(), rel * ref.std().item()
+    assert err <= tol, f"{what}: max|d| {err:.4g} > {tol:.4g} ({rel} x std {ref.std():.4g})"
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    return build(TINY_CONFIG, 0)
+
+
+def test_loaded_native_library():
+    assert os.path.basename(_lib.LIB_PATH) == "libstorygen_b200.so" and _lib.load() is not None
+
+
+def test_unet_matches_reference_golden(tiny):
+    _, mod = tiny
+    g = torch.load(os.path.join(GOLD, "unet_tiny.pt"))
+    x, t, txt = unet_inputs(g["n"], TINY_CONFIG["cross_attention_dim"], seed=g["input_seed"])
+    before = _lib.launch_count()
+    out = mod(x.cuda(), t.cuda(), txt.cuda())
+    assert _lib.launch_count() > before, "no native kernel was launched"
+    s, taps = out.sample, out.img_dif_conditions
+    assert s.dtype == torch.float32 and s.shape == x.shape and len(taps) == 16
+    check(s, g["feature_sample"], what="feature-pass sample")
+    for k, v in taps.items():
+        assert list(v.shape) == g["taps_shape"][k]
+        ref = g["taps_sub"][k]
+        assert (sub(v.float().cpu()) - ref).abs().max() <= REL * ref.std(), k
+    # denoise pass on the reference's own taps (fp32 golden only stores a subsample -> rebuild with the oracle)
+    ora = tiny[0]
+    o_taps = ora(x, t, txt)[1]
+    cond = cond_from_taps(o_taps, g["R"])
+    s2, d = mod(x.cuda(), 981, txt.cuda(), image_hidden_states={k: v.cuda() for k, v in cond.items()}, return_dict=False)
+    assert d == {}
+    check(s2, g["denoise_sample"], what="denoise-pass sample")
+
+
+@pytest.mark.parametrize("hw,n,R", [(64, 3, 3), (32, 2, 1), (96, 1, 2)])
+def test_unet_vs_oracle_resolutions(tiny, hw, n, R):
+    ora, mod = tiny
+    x, t, txt = unet_inputs(n, TINY_CONFIG["cross_attention_dim"], hw=hw, seed=31 + hw)
+    os_, ot = ora(x, t, txt)
+    cs, ct = mod(x.cuda(), t.cuda(), txt.cuda(), return_dict=False)
+    check(cs, os_, what="sample")
+    for k in ot:
+        check(ct[k], ot[k], what=k)
+    cond = cond_from_taps(ot, R)
+    o2 = ora(x, t, txt, cond)[0]
+    c2 = mod(x.cuda(), t.cuda(), txt.cuda(), image_hidden_states={k: v.cuda() for k, v in cond.items()}, return_dict=False)[0]
+    check(c2, o2, what="denoise sample")
+
+
+def test_unet_batch_invariance_and_timestep_forms(tiny):
+    _, mod = tiny
+    x, t, txt = unet_inputs(3, TINY_CONFIG["cross_attention_dim"], seed=5)
+    full = mod(x.cuda(), t.cuda(), txt.cuda(), return_dict=False)[0]
+    one = mod(x[1:2].cuda(), int(t[1]), txt[1:2].cuda(), return_dict=False)[0]
+    assert torch.equal(full[1:2], one), "lanes must not influence each other (CFG lane de-duplication relies on it)"
+    zero_d = mod(x[1:2].cuda(), torch.tensor(int(t[1])), txt[1:2].cuda(), return_dict=False)[0]
+    assert torch.equal(zero_d, one)
+
+
+def test_full_size_sd15_unet_vs_oracle():
+    ora, mod = build(SD15_CONFIG, 1)
+    x, t, txt = unet_inputs(1, 768, seed=77)
+    os_, ot = ora(x, t, txt)
+    cs, ct = mod(x.cuda(), t.cuda(), txt.cuda(), return_dict=False)
+    check(cs, os_, what="sample")
+    for k in ot:
+        check(ct[k], ot[k], what=k)
+    cond = cond_from_taps(ot, 3)
+    o2 = ora(x, 981, txt, cond)[0]
+    c2 = mod(x.cuda(), 981, txt.cuda(), image_hidden_states={k: v.cuda() for k, v in cond.items()}, return_dict=False)[0]
+    check(c2, o2, what="denoise sample R=3")
+    del mod
+    torch.cuda.empty_cache()
+
+
+def test_denoise_loop_vs_oracle_and_graph_equals_eager(tiny):
+    ora, mod = tiny
+    inp = sampler.synthetic_inputs(batch=2, num_frames=2, text_dim=TINY_CONFIG["cross_attention_dim"])
+    steps, g_txt, g_img = 3, 2.0, 1.5  # mild guidance keeps random-weight trajectories O(1)
+    ref = sampler.denoise(ora, num_inference_steps=steps, guidance_scale=g_txt, image_guidance_scale=g_img, **inp)
+    pipe = StableDiffusionPipeline(None, None, None, mod, DDIMScheduler())
+    cu = {k: ([t.cuda() for t in v] if isinstance(v, list) else v.cuda()) for k, v in inp.items()}
+    pipe.use_cuda_graph = False
+    eager = pipe.denoise(num_inference_steps=steps, guidance_scale=g_txt, image_guidance_scale=g_img, **cu)
+    pipe.use_cuda_graph = True
+    graphed = pipe.denoise(num_inference_steps=steps, guidance_scale=g_txt, image_guidance_scale=g_img, **cu)
+    assert torch.equal(eager, graphed), "CUDA-graph replay must be bit-identical to eager launches"
+    # three steps of bf16 noise compound; gate at 0.15 x std of the final latent
+    check(eager, ref, rel=0.15, what="3-step latents")
+
+
+def test_pipeline_call_matches_reference_pipeline_golden(tiny):
+    """StableDiffusionPipeline.__call__ with the stub tokenizer/CLIP/VAE vs the latents the REFERENCE
+    pipeline produced with the same stubs and seeds (tests/golden/pipeline_tiny.pt)."""
+    from oracle.make_golden import PIPE_ARGS, pipeline_images
+    from oracle.stubs import StubTextEncoder, StubTokenizer, StubVAE
+    _, mod = tiny
+    g = torch.load(os.path.join(GOLD, "pipeline_tiny.pt"))
+    pipe = StableDiffusionPipeline(StubVAE().cuda(), StubTextEncoder(TINY_CONFIG["cross_attention_dim"], g["text_seed"]).cuda(),
+                                   StubTokenizer(), mod, DDIMScheduler())
+    # the reference drew its RNG on the CPU; reproduce the same draws and hand them over
+    from test_oracle import stub_pipeline_inputs
+    inp = stub_pipeline_inputs(g, TINY_CONFIG["cross_attention_dim"])
+    lat = []
+    cu = {k: ([t.cuda() for t in v] if isinstance(v, list) else v.cuda()) for k, v in inp.items()}
+    pipe.denoise(num_inference_steps=PIPE_ARGS["num_inference_steps"], guidance_scale=PIPE_ARGS["guidance_scale"],
+                 image_guidance_scale=PIPE_ARGS["image_guidance_scale"], stage=PIPE_ARGS["stage"],
+                 callback=lambda s, t, l: lat.append(l.clone()), **cu)
+    for got, ref in zip(lat, g["latents_step"]):
+        check(got, ref, rel=0.15, what="pipeline latents")
+    # and the full __call__ surface runs end to end (its RNG stream is the device's, so only shape/finite)
+    res = pipe(image_prompt=pipeline_images(g["image_seed"]).cuda(), output_type="np", **PIPE_ARGS)
+    img = res.images
+    assert img.shape == (1, 512, 512, 3) and bool((img == img).all())
