@@ -82,59 +82,81 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_denoise_step_seconds(R: int, threads: int, repeats: int = 1):
-    """The reference's algorithm on the host: ONE full denoising step at B=1 (R feature passes + 1 denoise
-    pass over the 3 CFG lanes, 11.05 TFLOP at R=3) with the fp32 oracle (asserted equal to the
-    reference's model/*.py in tests/test_oracle.py).  Attention uses SDPA, not the materialising baddbmm."""
-    import torch
+def usable_cores() -> int:
+    """Cores this process may actually use (affinity mask and cgroup quota), not the box's core count."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
 
-    from oracle import sampler
-    from oracle.unet import SD15_CONFIG, OracleUNet
 
-    torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    with torch.no_grad():
-        net = OracleUNet(**SD15_CONFIG).eval()
-        inp = sampler.synthetic_inputs(1, R)
-        acp = sampler.alphas_cumprod()
-        times = []
-        for _ in range(repeats):
+class CpuReference:
+    """The reference's algorithm on the host cores: the fp32 oracle (asserted equal to the reference's
+    model/*.py in tests/test_oracle.py; the reference itself needs diffusers==0.13.1, absent offline).
+    One SAMPLE = one feature-pass UNet call + one denoise-pass UNet call (R prior frames) for ONE CFG lane
+    (0.80 + 1.27 TFLOP at R=3).  A denoising step of one image is 3 lanes x (R feature + 1 denoise) calls,
+    every lane independent, so  t_step = 3 * (R * t_feature + t_denoise)  and images/s = 1 / (steps * t_step).
+    Attention uses SDPA (same math as the default baddbmm path, without materialising 4.8 GB of scores)."""
+
+    def __init__(self, R: int, threads: int):
+        import torch
+
+        from oracle import sampler
+        from oracle.unet import SD15_CONFIG, OracleUNet
+        self.torch, self.R = torch, R
+        torch.set_num_threads(threads)
+        torch.manual_seed(0)
+        with torch.no_grad():
+            self.net = OracleUNet(**SD15_CONFIG).eval()
+        self.inp = sampler.synthetic_inputs(1, R)
+        self.acp = sampler.alphas_cumprod()
+        self.sampler = sampler
+
+    def sample_seconds(self):
+        torch, inp, s = self.torch, self.inp, self.sampler
+        with torch.no_grad():
             t0 = time.perf_counter()
-            t = 981
-            conds = []
-            for i, ft in enumerate(sampler.feature_timesteps(t, R, "auto-regressive")):
-                tt = torch.full((1,), ft, dtype=torch.long)
-                nf = sampler.add_noise(inp["frame_latents"][i], inp["noise"], tt, acp)
-                nz = sampler.add_noise(inp["zero_latents"], inp["noise"], tt, acp)
-                txt = torch.cat([inp["prev_uncond"][i], inp["prev_cond"][i], inp["prev_cond"][i]])
-                conds.append(net(torch.cat([nz, nf, nf]), ft, txt, None)[1])
-            img = {k: torch.cat([c[k] for c in conds], 1) for k in conds[0]}
-            txt = torch.cat([inp["text_uncond"], inp["text_uncond"], inp["text_cond"]])
-            eps = net(torch.cat([inp["latents"]] * 3), t, txt, img)[0]
-            e_u, e_i, e_a = eps.chunk(3)
-            sampler.ddim_step(e_u + 3.5 * (e_i - e_u) + 7.0 * (e_a - e_i), t, inp["latents"], 50, acp)
-            times.append(time.perf_counter() - t0)
-    return times
+            ft = s.feature_timesteps(981, self.R, "auto-regressive")[0]
+            x = s.add_noise(inp["frame_latents"][0], inp["noise"], torch.full((1,), ft, dtype=torch.long), self.acp)
+            taps = self.net(x, ft, inp["prev_cond"][0], None)[1]
+            t_feat = time.perf_counter() - t0
+            img = {k: torch.cat([v] * self.R, 1) for k, v in taps.items()}
+            t0 = time.perf_counter()
+            self.net(inp["latents"], 981, inp["text_cond"], img)
+            t_den = time.perf_counter() - t0
+        return t_feat, t_den
+
+    def describe(self, t_feat, t_den, ddim_steps, n):
+        t_step = 3 * (self.R * t_feat + t_den)
+        return t_step, (f"{n} x [one feature-pass + one denoise-pass UNet call, 1 CFG lane, R={self.R}: "
+                        f"{t_feat:.2f} s + {t_den:.2f} s]; t_step = 3 lanes x (R x feature + denoise) = {t_step:.1f} s; "
+                        f"images/s = 1/({ddim_steps} x t_step); fp32 oracle == reference model/*.py, SDPA attention")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    times = cpu_denoise_step_seconds(args.frames, threads, repeats=max(1, args.warmup > 0) + args.steps)
-    times = times[1:] if len(times) > args.steps else times
-    t_step = sum(times) / len(times)
+    threads = usable_cores()
+    ref = CpuReference(args.frames, threads)
+    if args.warmup > 0:
+        ref.sample_seconds()
+    ts = [ref.sample_seconds() for _ in range(args.steps)]
+    t_feat, t_den = sum(t[0] for t in ts) / len(ts), sum(t[1] for t in ts) / len(ts)
+    t_step, desc = ref.describe(t_feat, t_den, args.ddim_steps, len(ts))
     value = 1.0 / (args.ddim_steps * t_step)
     line = {
         "impl": "reference", "metric": "images_per_sec_512px_3ref_50step", "value": value, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.ddim_steps * t_step,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.ddim_steps * t_step * args.batch,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{len(times)} x one full denoising step at B=1 (R={args.frames} feature passes + 1 "
-                                   f"denoise pass, 3 CFG lanes, {tflop_per_image(args.frames, 1):.2f} TFLOP) = "
-                                   f"{t_step:.2f} s; images/s = 1/({args.ddim_steps} x step); fp32 oracle == reference "
-                                   "model/*.py (the reference itself needs diffusers==0.13.1, absent offline)"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -204,6 +226,7 @@ def run_ours(args, rank, local_rank, world):
     import torch.distributed as dist
 
     from storygen_b200 import DDIMScheduler, StableDiffusionPipeline, UNet2DConditionModel, _lib
+    from storygen_b200.distributed import gather_latents, shard_range
     from storygen_b200.synthetic import input_bytes, random_init_, synthetic_inputs, to_device
 
     torch.cuda.set_device(local_rank)
@@ -217,16 +240,16 @@ def run_ours(args, rank, local_rank, world):
         unet = UNet2DConditionModel(cross_attention_dim=768)
     unet = random_init_(unet.to_empty(device=dev), seed=0).eval()
     pipe = StableDiffusionPipeline(None, None, None, unet, DDIMScheduler())
-    host_in = synthetic_inputs(B, R, latent_hw=args.latent, first_image=rank * B, pin=True)
+    first, _ = shard_range(world * B, rank, world)
+    host_in = synthetic_inputs(B, R, latent_hw=args.latent, first_image=first, pin=True)
     dev_in = to_device(host_in, dev)
     kw = dict(num_inference_steps=args.ddim_steps, guidance_scale=7.0, image_guidance_scale=3.5, stage="auto-regressive")
-    gathered = torch.empty(world * B, 4, args.latent, args.latent, device=dev) if world > 1 else None
     host_out = torch.empty(B, 4, args.latent, args.latent).pin_memory()
 
     def one_step(inputs, to_host):
         lat = pipe.denoise(**inputs, **kw)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, lat.contiguous())
+        lat_all = gather_latents(lat, world * B)  # the path's only collective (2 MiB at 8 x B=8)
+        assert lat_all.shape[0] == world * B
         if to_host:
             host_out.copy_(lat, non_blocking=True)
         return lat
@@ -271,12 +294,12 @@ def run_ours(args, rank, local_rank, world):
         model_tf = tf_img * value / world  # per GPU, reference-equivalent FLOPs (de-duplicated lane NOT credited)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            ts = cpu_denoise_step_seconds(R, threads, repeats=1)
-            cpu = {"value": 1.0 / (args.ddim_steps * ts[0]), "unit": "images/s", "cores": threads, "kind": "port",
-                   "sample": f"one full denoising step at B=1 ({tflop_per_image(R, 1):.2f} TFLOP: {R} feature passes + 1 "
-                             f"denoise pass over 3 CFG lanes) = {ts[0]:.2f} s with the fp32 oracle (== reference "
-                             f"model/*.py, tests/test_oracle.py); images/s = 1/({args.ddim_steps} x step)"}
+            threads = usable_cores()
+            ref = CpuReference(R, threads)
+            t_feat, t_den = ref.sample_seconds()
+            t_step, desc = ref.describe(t_feat, t_den, args.ddim_steps, 1)
+            cpu = {"value": 1.0 / (args.ddim_steps * t_step), "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": desc}
         main = dict(roof["conv3x3_320_L0"])
         line = {
             "metric": "images_per_sec_512px_3ref_50step", "value": value, "unit": "images/s", "n_gpus": world,

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 4
+#define SG_ABI_VERSION 5
 
 #define SG_ERR_SHAPE (-1)   /* unsupported / inconsistent shape            */
 #define SG_ERR_ALIGN (-2)   /* pointer or stride not 16-byte aligned        */
@@ -74,6 +74,7 @@ typedef struct sg_seg {
 
 #define SG_EPI_LINEAR 0 /* out = acc + bias + lane_bias + res_scale * residual            */
 #define SG_EPI_GEGLU 1  /* B rows interleaved [16 value | 16 gate]; out = v * gelu_erf(g) */
+#define SG_EPI_NCHW_F32 2 /* N == 32 (zero-padded weight rows); out = fp32 (n, out_channels, h, w) */
 
 typedef struct sg_gemm_args {
   int32_t num_src;
@@ -88,6 +89,7 @@ typedef struct sg_gemm_args {
   int64_t N, Ktot;
   /* epilogue */
   int32_t mode;
+  int32_t out_channels; /* SG_EPI_NCHW_F32 only */
   float res_scale;
   const float* bias;      /* [N] (pre-activation columns) or NULL */
   const float* lane_bias; /* [out_n, ld_lane_bias] or NULL (per-image bias: time embedding) */
@@ -163,13 +165,12 @@ int sg_small_linear(const float* x, int32_t n, int32_t k, const void* w, const f
 /* Nearest-neighbour 2x upsample NHWC bf16 (Upsample2D, model/unet_2d_blocks.py:581-584,656-658). */
 int sg_upsample2x(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream);
 
-/* conv_in: 3x3 conv, NCHW fp32 (cin<=8) -> NHWC bf16 (model/unet_2d_condition.py:124,411). */
-int sg_conv_in(const float* x_nchw, int32_t n, int32_t cin, int32_t h, int32_t w, const float* wgt,
-               const float* bias, int32_t cout, void* y_nhwc, void* stream);
-/* conv_out: 3x3 conv NHWC bf16 (already GN+SiLU'd) -> NCHW fp32, cout<=8
- * (model/unet_2d_condition.py:268,480). */
-int sg_conv_out(const void* x_nhwc, int32_t n, int32_t cin, int32_t h, int32_t w, const float* wgt,
-                const float* bias, int32_t cout, float* y_nchw, void* stream);
+/* conv_in front end (model/unet_2d_condition.py:124,411): 3x3 patches of the NCHW fp32 latent
+ * (cin <= 7) -> bf16 rows (n*h*w, 64): column (ky*3+kx)*cin + ci, zero padded.  conv_in itself is then
+ * one sg_gemm with K = 64.  conv_out (model/unet_2d_condition.py:268,480) is sg_gemm with the
+ * SG_EPI_NCHW_F32 epilogue. */
+int sg_im2col3x3_nchw(const float* x_nchw, int32_t n, int32_t cin, int32_t h, int32_t w, void* patches,
+                      void* stream);
 
 /* x_t = sqrt(acp[t]) * x + sqrt(1 - acp[t]) * eps  (DDIMScheduler.add_noise at
  * model/pipeline.py:420-424); per-image timestep index t[n]; all fp32; numel per image = chw. */

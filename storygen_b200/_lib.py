@@ -11,16 +11,17 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstorygen_b200.so")
 
-SG_ABI_VERSION = 4
+SG_ABI_VERSION = 5
 SG_MAX_SRC = 4
 SG_MAX_SEGS = 24
 SG_EPI_LINEAR = 0
 SG_EPI_GEGLU = 1
+SG_EPI_NCHW_F32 = 2
 
 EXPORTS = [
     "sg_abi_version", "sg_sizeof_gemm_args", "sg_sizeof_attn_args", "sg_launch_count", "sg_error_string",
     "sg_gemm", "sg_attention", "sg_groupnorm_ws_floats", "sg_groupnorm_stats", "sg_groupnorm_apply",
-    "sg_layernorm", "sg_timestep_features", "sg_small_linear", "sg_upsample2x", "sg_conv_in", "sg_conv_out",
+    "sg_layernorm", "sg_timestep_features", "sg_small_linear", "sg_upsample2x", "sg_im2col3x3_nchw",
     "sg_add_noise", "sg_cfg_ddim_step",
 ]
 
@@ -38,7 +39,7 @@ class SgGemmArgs(C.Structure):
     _fields_ = [("num_src", C.c_int32), ("num_segs", C.c_int32), ("src", SgSrc * SG_MAX_SRC),
                 ("segs", SgSeg * SG_MAX_SEGS), ("out_w", C.c_int32), ("out_h", C.c_int32), ("out_n", C.c_int32),
                 ("bw", C.c_int32), ("bh", C.c_int32), ("bn", C.c_int32), ("b", C.c_void_p), ("N", C.c_int64),
-                ("Ktot", C.c_int64), ("mode", C.c_int32), ("res_scale", C.c_float), ("bias", C.c_void_p),
+                ("Ktot", C.c_int64), ("mode", C.c_int32), ("out_channels", C.c_int32), ("res_scale", C.c_float), ("bias", C.c_void_p),
                 ("lane_bias", C.c_void_p), ("ld_lane_bias", C.c_int64), ("residual", C.c_void_p),
                 ("ldr", C.c_int64), ("out", C.c_void_p), ("ldo", C.c_int64)]
 
@@ -89,8 +90,7 @@ def load():
     lib.sg_timestep_features.argtypes = [vp, i32, i32, vp, vp]
     lib.sg_small_linear.argtypes = [vp, i32, i32, vp, vp, i32, i32, i32, vp, vp]
     lib.sg_upsample2x.argtypes = [vp, i32, i32, i32, i32, vp, vp]
-    lib.sg_conv_in.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]
-    lib.sg_conv_out.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]
+    lib.sg_im2col3x3_nchw.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     lib.sg_add_noise.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     lib.sg_cfg_ddim_step.argtypes = [vp, vp, i32, i32, f32, f32, vp, vp]
     _lib = lib

@@ -269,92 +269,31 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, int n, int h, int
   }
 }
 
-// thread = (pixel, 8 output channels); weights [cout][cin][3][3] fp32
-__global__ void conv_in_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
-                               const float* __restrict__ wgt, const float* __restrict__ bias, int cout,
-                               bf16* __restrict__ y) {
-  const int V = cout / 8;
-  const long long total = static_cast<long long>(n) * h * w * V;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int vc = static_cast<int>(i % V);
-  long long p = i / V;
-  const int px = static_cast<int>(p % w);
-  p /= w;
-  const int py = static_cast<int>(p % h);
-  const int nn = static_cast<int>(p / h);
-  float acc[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = bias[vc * 8 + k];
-  for (int ci = 0; ci < cin; ++ci)
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = py + ky - 1;
-      if (yy < 0 || yy >= h) continue;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = px + kx - 1;
-        if (xx < 0 || xx >= w) continue;
-        const float xv = x[((static_cast<long long>(nn) * cin + ci) * h + yy) * w + xx];
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          acc[k] = fmaf(xv, __ldg(wgt + ((static_cast<long long>(vc * 8 + k) * cin + ci) * 3 + ky) * 3 + kx), acc[k]);
-      }
-    }
-  *reinterpret_cast<uint4*>(y + ((static_cast<long long>(nn) * h + py) * w + px) * cout + vc * 8) = pack8(acc);
-}
-
-// one warp per output pixel; weights [cout][cin][3][3] fp32 re-laid in smem as [tap][cout][cin]
-__global__ void conv_out_kernel(const bf16* __restrict__ x, int n, int cin, int h, int w,
-                                const float* __restrict__ wgt, const float* __restrict__ bias, int cout,
-                                float* __restrict__ y) {
-  extern __shared__ float ws[];  // [9][cout][cin]
-  for (int i = threadIdx.x; i < 9 * cout * cin; i += blockDim.x) {
-    const int ci = i % cin;
-    const int co = (i / cin) % cout;
-    const int tap = i / (cin * cout);
-    ws[i] = wgt[(static_cast<long long>(co) * cin + ci) * 9 + tap];
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long pix = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// one thread per pixel: gathers its 3x3 x cin patch (zero padded) into one 128-byte bf16 row
+__global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
+                                      bf16* __restrict__ out) {
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pix >= static_cast<long long>(n) * h * w) return;
   const int px = static_cast<int>(pix % w);
   const int py = static_cast<int>((pix / w) % h);
   const int nn = static_cast<int>(pix / (static_cast<long long>(w) * h));
-  float acc[8];
+  __align__(16) bf16 row[64];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  const int V = cin / 8;
+  for (int i = 0; i < 64; ++i) row[i] = __float2bfloat16(0.f);
   for (int ky = 0; ky < 3; ++ky) {
     const int yy = py + ky - 1;
     if (yy < 0 || yy >= h) continue;
     for (int kx = 0; kx < 3; ++kx) {
       const int xx = px + kx - 1;
       if (xx < 0 || xx >= w) continue;
-      const bf16* xp = x + ((static_cast<long long>(nn) * h + yy) * w + xx) * cin;
-      const float* wt = ws + (ky * 3 + kx) * cout * cin;
-      for (int v = lane; v < V; v += 32) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(xp + v * 8)), f);
-#pragma unroll
-        for (int co = 0; co < 8; ++co) {
-          if (co < cout) {
-            const float* wc = wt + co * cin + v * 8;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[co] = fmaf(f[k], wc[k], acc[co]);
-          }
-        }
-      }
+      for (int ci = 0; ci < cin; ++ci)
+        row[(ky * 3 + kx) * cin + ci] = __float2bfloat16(x[((static_cast<long long>(nn) * cin + ci) * h + yy) * w + xx]);
     }
   }
+  uint4* dst = reinterpret_cast<uint4*>(out + pix * 64);
+  const uint4* src = reinterpret_cast<const uint4*>(row);
 #pragma unroll
-  for (int co = 0; co < 8; ++co) {
-    if (co < cout) {
-      float a = acc[co];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0) y[((static_cast<long long>(nn) * cout + co) * h + py) * w + px] = a + bias[co];
-    }
-  }
+  for (int i = 0; i < 8; ++i) dst[i] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -473,33 +412,13 @@ extern "C" int sg_upsample2x(const void* x, int32_t n, int32_t h, int32_t w, int
   SG_LAUNCH_END();
 }
 
-extern "C" int sg_conv_in(const float* x_nchw, int32_t n, int32_t cin, int32_t h, int32_t w, const float* wgt,
-                          const float* bias, int32_t cout, void* y_nhwc, void* stream) {
-  if (!x_nchw || !wgt || !bias || !y_nhwc) return SG_ERR_ARG;
-  if (cout % 8) return SG_ERR_SHAPE;
-  const long long total = static_cast<long long>(n) * h * w * (cout / 8);
-  conv_in_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x_nchw, n, cin, h, w, wgt, bias, cout, static_cast<bf16*>(y_nhwc));
-  SG_LAUNCH_END();
-}
-
-extern "C" int sg_conv_out(const void* x_nhwc, int32_t n, int32_t cin, int32_t h, int32_t w, const float* wgt,
-                           const float* bias, int32_t cout, float* y_nchw, void* stream) {
-  if (!x_nhwc || !wgt || !bias || !y_nchw) return SG_ERR_ARG;
-  if (cin % 8 || cout > 8) return SG_ERR_SHAPE;
-  const size_t smem = static_cast<size_t>(9) * cout * cin * sizeof(float);
-  if (smem > 200 * 1024) return SG_ERR_SHAPE;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
+extern "C" int sg_im2col3x3_nchw(const float* x_nchw, int32_t n, int32_t cin, int32_t h, int32_t w, void* patches,
+                                 void* stream) {
+  if (!x_nchw || !patches) return SG_ERR_ARG;
+  if (cin < 1 || 9 * cin > 64) return SG_ERR_SHAPE;
   const long long pixels = static_cast<long long>(n) * h * w;
-  const int warps = 16;
-  conv_out_kernel<<<static_cast<unsigned>((pixels + warps - 1) / warps), warps * 32, smem,
-                    static_cast<cudaStream_t>(stream)>>>(static_cast<const bf16*>(x_nhwc), n, cin, h, w, wgt, bias,
-                                                         cout, y_nchw);
+  im2col3x3_nchw_kernel<<<static_cast<unsigned>((pixels + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_nchw, n, cin, h, w, static_cast<bf16*>(patches));
   SG_LAUNCH_END();
 }
 

@@ -30,6 +30,7 @@ struct GemmKParams {
   int num_n_tiles;
   int N;
   int mode;
+  int out_channels;  // SG_EPI_NCHW_F32: number of valid output channels (<= 32)
   float res_scale;
   const float* bias;
   const float* lane_bias;
@@ -217,7 +218,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
               f[4 * j + 3] += b.w;
             }
           }
-          if (!geglu) {
+          if (p.mode == SG_EPI_NCHW_F32) {
+            // final conv: fp32 NCHW store of the first out_channels columns (coalesced along x)
+            if (c == 0) {
+              float* of = reinterpret_cast<float*>(p.out);
+              const long long plane = static_cast<long long>(p.out_h) * p.out_w;
+              const long long base = static_cast<long long>(n) * p.out_channels * plane + static_cast<long long>(y) * p.out_w + x;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < p.out_channels) of[base + j * plane] = f[j];
+            }
+          } else if (!geglu) {
             if (p.residual != nullptr) {
               const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col0);
 #pragma unroll
@@ -307,8 +318,9 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
     return SG_ERR_ARG;
   if (a->bw * a->bh * a->bn != kBM || a->bw > 256 || a->bh > 256 || a->bn > 256) return SG_ERR_SHAPE;
   if (a->N % 32 != 0 || a->Ktot % kBK != 0) return SG_ERR_SHAPE;
-  if (a->mode != SG_EPI_LINEAR && a->mode != SG_EPI_GEGLU) return SG_ERR_ARG;
-  if ((reinterpret_cast<uintptr_t>(a->out) & 15) || (a->ldo % 8) ||
+  if (a->mode != SG_EPI_LINEAR && a->mode != SG_EPI_GEGLU && a->mode != SG_EPI_NCHW_F32) return SG_ERR_ARG;
+  if (a->mode == SG_EPI_NCHW_F32 && (a->out_channels < 1 || a->out_channels > 32 || a->N != 32)) return SG_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(a->out) & 15) || (a->mode != SG_EPI_NCHW_F32 && (a->ldo % 8)) ||
       (a->residual && ((reinterpret_cast<uintptr_t>(a->residual) & 15) || (a->ldr % 8))))
     return SG_ERR_ALIGN;
 
@@ -359,6 +371,7 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   kp.num_n_tiles = static_cast<int>((a->N + bn_tile - 1) / bn_tile);
   kp.N = static_cast<int>(a->N);
   kp.mode = a->mode;
+  kp.out_channels = a->out_channels;
   kp.res_scale = a->res_scale;
   kp.bias = a->bias;
   kp.lane_bias = a->lane_bias;

@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import ops
-from ._lib import SG_EPI_GEGLU
+from ._lib import SG_EPI_GEGLU, SG_EPI_NCHW_F32
 from .ops import BF16, Src, taps3x3
 
 F32 = torch.float32
@@ -107,7 +107,12 @@ class UNetEngine:
     def _pack(self):
         m = self.model
         tw, tb = [], []
-        self.conv_in = (self._f32(m.conv_in.weight), self._f32(m.conv_in.bias))
+        ci = m.conv_in.weight.shape[1]
+        if 9 * ci > 64:
+            raise NotImplementedError("in_channels > 7")
+        w_in = torch.zeros(m.conv_in.weight.shape[0], 64, dtype=F32, device=self.dev)
+        w_in[:, :9 * ci] = self._conv3(m.conv_in.weight).to(self.dev, F32)  # column (ky*3+kx)*cin + ci
+        self.conv_in = (self._bf(w_in), self._f32(m.conv_in.bias))
         te = m.time_embedding
         self.time = (self._bf(te.linear_1.weight), self._f32(te.linear_1.bias), self._bf(te.linear_2.weight),
                      self._f32(te.linear_2.bias))
@@ -137,7 +142,14 @@ class UNetEngine:
         self.temb_w = self._bf(torch.cat(tw, 0))
         self.temb_b = self._f32(torch.cat(tb, 0))
         self.norm_out = (self._f32(m.conv_norm_out.weight), self._f32(m.conv_norm_out.bias))
-        self.conv_out = (self._f32(m.conv_out.weight), self._f32(m.conv_out.bias))
+        co = m.conv_out.weight.shape[0]
+        if co > 32:
+            raise NotImplementedError("out_channels > 32")
+        w_out = torch.zeros(32, 9 * m.conv_out.weight.shape[1], dtype=F32, device=self.dev)
+        w_out[:co] = self._conv3(m.conv_out.weight).to(self.dev, F32)
+        b_out = torch.zeros(32, dtype=F32, device=self.dev)
+        b_out[:co] = m.conv_out.bias.detach().to(self.dev, F32)
+        self.conv_out = (self._bf(w_out), b_out, co)
 
     # ------------------------------------------------------------------------------------------
     # building blocks
@@ -308,7 +320,9 @@ class UNetEngine:
                 taps[key] = tap
             return out
 
-        x = ops.conv_in(sample, self.conv_in[0], self.conv_in[1], self._new(n, h, w, boc0))
+        patches = ops.im2col3x3_nchw(sample, self._new(n * h * w, 64))
+        x = self._new(n, h, w, boc0)
+        ops.linear(patches, self.conv_in[0], x.view(n * h * w, boc0), bias=self.conv_in[1])
         skips = [x]
         hh, ww = h, w
         for i, blk in enumerate(self.down):
@@ -333,6 +347,7 @@ class UNetEngine:
                 x = self._upsample(blk["up"], x, n, hh, ww)
                 hh, ww = hh * 2, ww * 2
         xn = self._gn(x.view(n, hh * ww, -1), None, n, hh * ww, self.norm_out, self.eps, True)
-        out = ops.conv_out(xn.view(n, hh, ww, -1), self.conv_out[0], self.conv_out[1],
-                           self._new(n, self.conv_out[0].shape[0], hh, ww, dtype=F32))
+        out = self._new(n, self.conv_out[2], hh, ww, dtype=F32)
+        ops.gemm([Src.nhwc(xn.view(n, hh, ww, -1))], taps3x3(0, xn.shape[-1]), (ww, hh, n), self.conv_out[0], out,
+                 bias=self.conv_out[1], mode=SG_EPI_NCHW_F32, out_channels=self.conv_out[2])
         return out, taps

@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import SG_EPI_GEGLU, SG_EPI_LINEAR, SgAttnArgs, SgGemmArgs
+from ._lib import SG_EPI_GEGLU, SG_EPI_LINEAR, SG_EPI_NCHW_F32, SgAttnArgs, SgGemmArgs
 
 BF16 = torch.bfloat16
 
@@ -70,7 +70,7 @@ def tile_box(w: int, h: int, n: int) -> Tuple[int, int, int]:
 def gemm(srcs: Sequence[Src], segs: Sequence[Tuple[int, int, int, int, int]], grid: Tuple[int, int, int],
          weight: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None,
          lane_bias: Optional[torch.Tensor] = None, ld_lane_bias: int = 0, residual: Optional[torch.Tensor] = None,
-         res_scale: float = 1.0, mode: int = SG_EPI_LINEAR) -> torch.Tensor:
+         res_scale: float = 1.0, mode: int = SG_EPI_LINEAR, out_channels: int = 0) -> torch.Tensor:
     """out[m, :] = epilogue(sum_k A[m, k] W[:, k]); see include/storygen_b200.h (sg_gemm).
     segs: (src, dx, dy, c0, nkb); grid: (out_w, out_h, out_n); weight: bf16 [N, Ktot]."""
     a = SgGemmArgs()
@@ -86,7 +86,8 @@ def gemm(srcs: Sequence[Src], segs: Sequence[Tuple[int, int, int, int, int]], gr
     a.out_w, a.out_h, a.out_n = grid
     a.bw, a.bh, a.bn = tile_box(*grid)
     _req(weight, BF16, "weight")
-    _req(out, BF16, "out")
+    _req(out, torch.float32 if mode == SG_EPI_NCHW_F32 else BF16, "out")
+    a.out_channels = out_channels
     a.b = weight.data_ptr()
     a.N, a.Ktot = weight.shape
     a.mode = mode
@@ -179,19 +180,13 @@ def upsample2x(x: torch.Tensor, out: torch.Tensor):
     return out
 
 
-def conv_in(x_nchw: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out_nhwc: torch.Tensor):
+def im2col3x3_nchw(x_nchw: torch.Tensor, out: torch.Tensor):
+    """(n, cin, h, w) fp32 -> (n*h*w, 64) bf16 rows of zero-padded 3x3 patches, column (ky*3+kx)*cin + ci."""
     _req(x_nchw, torch.float32, "sample")
     n, cin, h, ww = x_nchw.shape
-    _lib.check(_lib.load().sg_conv_in(x_nchw.data_ptr(), n, cin, h, ww, w.data_ptr(), b.data_ptr(), w.shape[0],
-                                      out_nhwc.data_ptr(), _stream()), "sg_conv_in")
-    return out_nhwc
-
-
-def conv_out(x_nhwc: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out_nchw: torch.Tensor):
-    n, h, ww, cin = x_nhwc.shape
-    _lib.check(_lib.load().sg_conv_out(x_nhwc.data_ptr(), n, cin, h, ww, w.data_ptr(), b.data_ptr(), w.shape[0],
-                                       out_nchw.data_ptr(), _stream()), "sg_conv_out")
-    return out_nchw
+    _lib.check(_lib.load().sg_im2col3x3_nchw(x_nchw.data_ptr(), n, cin, h, ww, out.data_ptr(), _stream()),
+               "sg_im2col3x3_nchw")
+    return out
 
 
 def add_noise(x: torch.Tensor, eps: torch.Tensor, acp: torch.Tensor, t: torch.Tensor, out: torch.Tensor):

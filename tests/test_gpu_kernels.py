@@ -172,14 +172,29 @@ def test_upsample_conv_in_out_and_scheduler_kernels():
     x = rnd(2, 8, 8, 64, seed=1)
     up = ops.upsample2x(x, torch.empty(2, 16, 16, 64, dtype=BF16, device=DEV))
     assert torch.equal(up, x.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    # conv_in = im2col of the 4-channel latent + one K=64 GEMM
     s = rnd(3, 4, 64, 64, seed=2, dtype=torch.float32)
     w, b = rnd(320, 4, 3, 3, scale=1 / 6, seed=3, dtype=torch.float32), rnd(320, seed=4, dtype=torch.float32)
-    y = ops.conv_in(s, w, b, torch.empty(3, 64, 64, 320, dtype=BF16, device=DEV))
-    close(y, F.conv2d(s, w, b, padding=1).permute(0, 2, 3, 1), rel=0.005, abs_=0.005)
+    patches = ops.im2col3x3_nchw(s, torch.empty(3 * 64 * 64, 64, dtype=BF16, device=DEV))
+    ref_p = F.unfold(s, 3, padding=1).view(3, 4, 9, 64 * 64).permute(0, 3, 2, 1).reshape(-1, 36)  # (ky*3+kx)*cin + ci
+    assert torch.equal(patches[:, :36], ref_p.to(BF16)) and bool((patches[:, 36:] == 0).all())
+    wp = torch.zeros(320, 64, device=DEV)
+    wp[:, :36] = w.permute(0, 2, 3, 1).reshape(320, 36)
+    y = torch.empty(3 * 64 * 64, 320, dtype=BF16, device=DEV)
+    ops.linear(patches, wp.to(BF16), y, bias=b)
+    ref = F.conv2d(s.to(BF16).float(), wp[:, :36].to(BF16).float().reshape(320, 3, 3, 4).permute(0, 3, 1, 2), b, padding=1)
+    close(y.view(3, 64, 64, 320), ref.permute(0, 2, 3, 1), rel=0.01, abs_=0.01)
+    # conv_out = implicit GEMM with the fp32 NCHW epilogue (weights zero-padded to 32 rows)
     xo = rnd(3, 64, 64, 320, seed=5)
     wo, bo = rnd(4, 320, 3, 3, scale=(9 * 320) ** -0.5, seed=6, dtype=torch.float32), rnd(4, seed=7, dtype=torch.float32)
-    yo = ops.conv_out(xo, wo, bo, torch.empty(3, 4, 64, 64, device=DEV))
-    close(yo, F.conv2d(xo.float().permute(0, 3, 1, 2), wo, bo, padding=1), rel=1e-3, abs_=1e-3)
+    wq = torch.zeros(32, 9 * 320, device=DEV)
+    wq[:4] = wo.permute(0, 2, 3, 1).reshape(4, -1)
+    bq = torch.zeros(32, device=DEV)
+    bq[:4] = bo
+    yo = torch.full((3, 4, 64, 64), float("nan"), device=DEV)
+    ops.gemm([Src.nhwc(xo)], taps3x3(0, 320), (64, 64, 3), wq.to(BF16), yo, bias=bq, mode=_lib.SG_EPI_NCHW_F32, out_channels=4)
+    refo = F.conv2d(xo.float().permute(0, 3, 1, 2), wq[:4].to(BF16).float().reshape(4, 3, 3, 320).permute(0, 3, 1, 2), bo, padding=1)
+    close(yo, refo, rel=1e-3, abs_=2e-3)
     # add_noise / cfg + ddim
     acp = torch.linspace(0.999, 0.005, 1000, device=DEV)
     lat, eps = rnd(4, 4, 64, 64, seed=8, dtype=torch.float32), rnd(4, 4, 64, 64, seed=9, dtype=torch.float32)

@@ -74,8 +74,7 @@ def test_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 4, 64, 64), 1, torch.zeros(1, 77, 64))
     with pytest.raises(RuntimeError, match="CUDA tensor"):
-        ops.conv_in(torch.zeros(1, 4, 8, 8), torch.zeros(64, 4, 3, 3), torch.zeros(64),
-                    torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16))
+        ops.im2col3x3_nchw(torch.zeros(1, 4, 8, 8), torch.zeros(64, 64, dtype=torch.bfloat16))
 
 
 def test_load_sdm_state_dict_and_save_roundtrip(tmp_path):
