@@ -9,16 +9,19 @@
 //   warps 2..5 : softmax      one thread per query row (= TMEM lane): S row -> registers, running max
 //                             with lazy rescale of the O row (only when the max grew by > 2^8),
 //                             exp2, row sum, P (bf16) written back over S, final O / l -> global.
+//   (QT == 2)  : warps 6..9 are a second softmax warpgroup for a second 128-query tile: the two tiles
+//                ping-pong on the tensor core and share every K/V tile (head dims <= 128).
 //
 // Q/K/V are read in place from (lane, token, channel) tensors; a head's [tokens x d] slice is fetched
 // as ceil(d/64) swizzle-128B atoms of 64 channels starting at channel h*d.  Channels past d inside the
 // last atom belong to the next head (or are TMA zero fill): they are neutralised by zeroing the padded
 // Q chunk in smem (QK^T) and by never storing the corresponding O columns (PV).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sg {
 
-constexpr int kAttnThreads = 192;
 constexpr int kAtomBytes = 128 * 128;  // [128 rows x 64 bf16], swizzle 128B
 
 struct AttnKParams {
@@ -30,55 +33,63 @@ struct AttnKParams {
   float scale_log2;  // scale * log2(e)
 };
 
-template <int D>
+// QT = number of 128-query tiles per CTA.
+//   QT == 1: S double-buffered (QK^T of tile j+1 overlaps the softmax of tile j); any head dim <= 192.
+//   QT == 2: two query tiles ping-pong on the tensor core, one S buffer each, two softmax warpgroups
+//            (2 warps per SM sub-partition keep the MUFU pipe busy), K/V tiles fetched once for both.
+template <int D, int QT>
 struct AttnCfg {
-  static constexpr int NA = (D + 63) / 64;   // 64-channel atoms per tile
-  static constexpr int KQ = (D + 15) / 16;   // k-steps of Q K^T
+  static constexpr int NA = (D + 63) / 64;  // 64-channel atoms per tile
+  static constexpr int KQ = (D + 15) / 16;  // k-steps of Q K^T
   static constexpr int kTileBytes = NA * kAtomBytes;
-  static constexpr int kSlots = (NA == 1) ? 8 : (NA == 2 ? 5 : 3);
-  static constexpr int kSmemBytes = kTileBytes * (1 + kSlots) + 1024 + 256;
-  static constexpr int kColS0 = 0, kColS1 = 128, kColO = 256;
+  static constexpr int kSlots = (QT == 2) ? (NA == 1 ? 8 : 4) : (NA == 1 ? 8 : (NA == 2 ? 5 : 3));
+  static constexpr int kFirstSoftmaxWarp = (QT == 2) ? 4 : 2;  // QT == 2: warpgroup 0 = {TMA, MMA, 2 idle}
+  static constexpr int kThreads = 32 * kFirstSoftmaxWarp + 128 * QT;
+  static constexpr int kSmemBytes = kTileBytes * (QT + kSlots) + 1024 + 256;
+  static constexpr int kColO = 256;
   static constexpr int kTmemCols = 512;
+  static_assert(QT == 1 || NA <= 2, "two query tiles need 2 x 64*NA O columns next to 256 S columns");
 };
 
-template <int D>
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
-  using Cfg = AttnCfg<D>;
+template <int D, int QT>
+__global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = AttnCfg<D, QT>;
   constexpr int NA = Cfg::NA;
+  constexpr int kSlots = Cfg::kSlots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* q_smem = smem;
-  uint8_t* kv_smem = smem + Cfg::kTileBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kTileBytes * (1 + Cfg::kSlots));
-  uint64_t* kv_full = bars;                    // [kSlots]
-  uint64_t* kv_empty = bars + Cfg::kSlots;     // [kSlots]
-  uint64_t* q_full = bars + 2 * Cfg::kSlots;   // TMA -> softmax warps
-  uint64_t* q_ready = q_full + 1;              // softmax warps -> MMA (Q pad zeroed)
-  uint64_t* s_full = q_ready + 1;              // [2] MMA -> softmax
-  uint64_t* p_full = s_full + 2;               // [2] softmax -> MMA
-  uint64_t* o_done = p_full + 2;               // MMA -> softmax (PV_j retired)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  uint8_t* kv_smem = smem + QT * Cfg::kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kTileBytes * (QT + kSlots));
+  uint64_t* kv_full = bars;              // [kSlots]
+  uint64_t* kv_empty = bars + kSlots;    // [kSlots]
+  uint64_t* q_full = bars + 2 * kSlots;  // [2] TMA -> softmax warps
+  uint64_t* q_ready = q_full + 2;        // [2] softmax warps -> MMA (Q pad zeroed)
+  uint64_t* s_full = q_ready + 2;        // [2] MMA -> softmax
+  uint64_t* p_full = s_full + 2;         // [2] softmax -> MMA
+  uint64_t* o_done = p_full + 2;         // [2] MMA -> softmax (PV retired)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128;
+  const int q0 = blockIdx.x * (128 * QT);
   const int head = blockIdx.y;
   const int img = blockIdx.z;
   const int T = (p.nk + 127) / 128;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::kSlots; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(q_full, 1);
-    mbar_init(q_ready, 4);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_ready[i], 4);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
+      mbar_init(&o_done[i], 1);
     }
-    mbar_init(o_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -87,14 +98,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < Cfg::kFirstSoftmaxWarp) {
+  // register re-distribution between warpgroups (QT == 2): warpgroup 0 = {TMA, MMA, 2 idle warps} gives its
+  // registers to the 8 softmax warps, which hold a 128-wide S row per thread
+  if constexpr (QT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0) {
     // ===================== TMA loader =====================
     if (lane == 0) {
       const int kv_img = (p.kv_map != nullptr) ? p.kv_map[img] : img;
-      mbar_arrive_expect_tx(q_full, Cfg::kTileBytes);
 #pragma unroll
-      for (int a = 0; a < NA; ++a)
-        tma_load_3d(q_smem + a * kAtomBytes, &p.q_map, q_full, head * D + 64 * a, q0, img);
+      for (int t = 0; t < QT; ++t) {
+        mbar_arrive_expect_tx(&q_full[t], Cfg::kTileBytes);
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          tma_load_3d(q_smem + t * Cfg::kTileBytes + a * kAtomBytes, &p.q_map, &q_full[t], head * D + 64 * a,
+                      q0 + 128 * t, img);
+      }
       int slot = 0;
       uint32_t phase = 0;
       auto load_tile = [&](const CUtensorMap* map, int key0) {
@@ -102,16 +121,25 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         mbar_arrive_expect_tx(&kv_full[slot], Cfg::kTileBytes);
 #pragma unroll
         for (int a = 0; a < NA; ++a)
-          tma_load_3d(kv_smem + slot * Cfg::kTileBytes + a * kAtomBytes, map, &kv_full[slot],
-                      head * D + 64 * a, key0, kv_img);
-        if (++slot == Cfg::kSlots) {
+          tma_load_3d(kv_smem + slot * Cfg::kTileBytes + a * kAtomBytes, map, &kv_full[slot], head * D + 64 * a,
+                      key0, kv_img);
+        if (++slot == kSlots) {
           slot = 0;
           phase ^= 1;
         }
       };
-      for (int s = 0; s <= T; ++s) {
-        if (s < T) load_tile(&p.k_map, s * 128);
-        if (s >= 1) load_tile(&p.v_map, (s - 1) * 128);
+      if constexpr (QT == 1) {
+        // consumption order of the MMA warp: K0 K1 V0 K2 V1 ...
+        for (int s = 0; s <= T; ++s) {
+          if (s < T) load_tile(&p.k_map, s * 128);
+          if (s >= 1) load_tile(&p.v_map, (s - 1) * 128);
+        }
+      } else {
+        // K0 V0 K1 V1 ...
+        for (int s = 0; s < T; ++s) {
+          load_tile(&p.k_map, s * 128);
+          load_tile(&p.v_map, s * 128);
+        }
       }
     }
   } else if (warp == 1) {
@@ -119,94 +147,147 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
-      int slot = 0;
-      uint32_t phase = 0;
-      const uint32_t q_addr = smem_u32(q_smem);
-      auto issue_qk = [&](int j) {
-        mbar_wait(&kv_full[slot], phase);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(kv_smem + slot * Cfg::kTileBytes);
-        const uint32_t d_tmem = tmem_base + ((j & 1) ? Cfg::kColS1 : Cfg::kColS0);
+      auto qk = [&](uint32_t q_addr, uint32_t k_addr, uint32_t s_col) {
 #pragma unroll
         for (int ks = 0; ks < Cfg::KQ; ++ks) {
           const uint32_t off = (ks >> 2) * kAtomBytes + (ks & 3) * 32;
-          umma_ss(d_tmem, make_smem_desc(q_addr + off, 16, 1024, kLayoutSW128),
+          umma_ss(tmem_base + s_col, make_smem_desc(q_addr + off, 16, 1024, kLayoutSW128),
                   make_smem_desc(k_addr + off, 16, 1024, kLayoutSW128), idesc_qk, ks != 0);
         }
-        umma_commit(&kv_empty[slot]);
-        umma_commit(&s_full[j & 1]);
-        if (++slot == Cfg::kSlots) {
-          slot = 0;
-          phase ^= 1;
-        }
       };
-      mbar_wait(q_ready, 0);
-      tc_fence_after();
-      issue_qk(0);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) issue_qk(j + 1);
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        mbar_wait(&kv_full[slot], phase);
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(kv_smem + slot * Cfg::kTileBytes);
-        const uint32_t p_tmem = tmem_base + ((j & 1) ? Cfg::kColS1 : Cfg::kColS0);
+      auto pv = [&](uint32_t p_col, uint32_t v_addr, uint32_t o_col, bool first) {
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             // V tile rows = keys (128 B pitch); 16 keys per k-step = 2048 B
-            umma_ts(tmem_base + Cfg::kColO + 64 * a, p_tmem + ks * 8,
-                    make_smem_desc(v_addr + a * kAtomBytes + ks * 2048, kAtomBytes, 1024, kLayoutSW128),
-                    idesc_pv, (j | ks) != 0);
+            umma_ts(tmem_base + o_col + 64 * a, tmem_base + p_col + ks * 8,
+                    make_smem_desc(v_addr + a * kAtomBytes + ks * 2048, kAtomBytes, 1024, kLayoutSW128), idesc_pv,
+                    !(first && ks == 0));
           }
         }
-        umma_commit(&kv_empty[slot]);
-        umma_commit(o_done);
-        if (++slot == Cfg::kSlots) {
-          slot = 0;
-          phase ^= 1;
+      };
+      if constexpr (QT == 1) {
+        int slot = 0;
+        uint32_t phase = 0;
+        const uint32_t q_addr = smem_u32(q_smem);
+        auto issue_qk = [&](int j) {
+          mbar_wait(&kv_full[slot], phase);
+          tc_fence_after();
+          qk(q_addr, smem_u32(kv_smem + slot * Cfg::kTileBytes), (j & 1) * 128);
+          umma_commit(&kv_empty[slot]);
+          umma_commit(&s_full[j & 1]);
+          if (++slot == kSlots) {
+            slot = 0;
+            phase ^= 1;
+          }
+        };
+        mbar_wait(&q_ready[0], 0);
+        tc_fence_after();
+        issue_qk(0);
+        for (int j = 0; j < T; ++j) {
+          if (j + 1 < T) issue_qk(j + 1);
+          mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+          mbar_wait(&kv_full[slot], phase);
+          tc_fence_after();
+          pv((j & 1) * 128, smem_u32(kv_smem + slot * Cfg::kTileBytes), Cfg::kColO, j == 0);
+          umma_commit(&kv_empty[slot]);
+          umma_commit(&o_done[0]);
+          if (++slot == kSlots) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      } else {
+        auto slot_of = [](int i) { return i % kSlots; };
+        auto phase_of = [](int i) { return static_cast<uint32_t>((i / kSlots) & 1); };
+        auto tile_addr = [&](int i) { return smem_u32(kv_smem + slot_of(i) * Cfg::kTileBytes); };
+        mbar_wait(&kv_full[slot_of(0)], phase_of(0));
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&q_ready[t], 0);
+          tc_fence_after();
+          qk(smem_u32(q_smem + t * Cfg::kTileBytes), tile_addr(0), t * 128);
+          umma_commit(&s_full[t]);
+        }
+        umma_commit(&kv_empty[slot_of(0)]);
+        for (int j = 0; j < T; ++j) {
+          const int iv = 2 * j + 1, ik = 2 * j + 2;
+          const bool more = (j + 1 < T);
+          mbar_wait(&kv_full[slot_of(iv)], phase_of(iv));
+          if (more) mbar_wait(&kv_full[slot_of(ik)], phase_of(ik));
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&p_full[t], j & 1);
+            tc_fence_after();
+            pv(t * 128, tile_addr(iv), Cfg::kColO + t * 64 * NA, j == 0);
+            umma_commit(&o_done[t]);
+            if (more) {
+              qk(smem_u32(q_smem + t * Cfg::kTileBytes), tile_addr(ik), t * 128);
+              umma_commit(&s_full[t]);
+            }
+          }
+          umma_commit(&kv_empty[slot_of(iv)]);
+          if (more) umma_commit(&kv_empty[slot_of(ik)]);
         }
       }
     }
+  }
   } else {
     // ===================== softmax / correction / epilogue =====================
+    if constexpr (QT == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;  // query row within the tile == TMEM lane
+    const int tq = (QT == 2) ? ((warp - Cfg::kFirstSoftmaxWarp) >> 2) : 0;  // query tile of this warpgroup
+    const int r = quarter * 32 + lane;                 // query row within the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t o_tmem = tmem_base + lane_base + Cfg::kColO + tq * 64 * NA;
+    uint8_t* my_q = q_smem + tq * Cfg::kTileBytes;
 
-    mbar_wait(q_full, 0);
+    mbar_wait(&q_full[tq], 0);
     if constexpr (D % 16 != 0) {
       // zero Q channels [D, D+8): 16-byte chunk (D/8 % 8) of atom D/64, XOR-swizzled by row
       constexpr int atom = D / 64;
       constexpr int chunk = (D % 64) / 8;
-      uint4* dst = reinterpret_cast<uint4*>(q_smem + atom * kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4));
+      uint4* dst = reinterpret_cast<uint4*>(my_q + atom * kAtomBytes + r * 128 + ((chunk ^ (r & 7)) << 4));
       *dst = make_uint4(0, 0, 0, 0);
       fence_proxy_async_smem();
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(q_ready);
+    if (lane == 0) mbar_arrive(&q_ready[tq]);
 
     float m_used = 0.f, l_run = 0.f;
-    for (int j = 0; j < T; ++j) {
-      const int b = j & 1;
-      mbar_wait(&s_full[b], (j >> 1) & 1);
+    // one KV tile of the online softmax; kMasked is only instantiated for the LAST tile (ragged nk), so the
+    // 128-element mask (ISETP + SEL per element once if-converted) stays out of the steady-state loop
+    auto softmax_tile = [&](const int j, auto masked_tag) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
+      const int sb = (QT == 2) ? tq : (j & 1);                         // S / P buffer
+      const uint32_t s_par = (QT == 2) ? (j & 1) : ((j >> 1) & 1);
+      uint64_t* od = &o_done[(QT == 2) ? tq : 0];
+      mbar_wait(&s_full[sb], s_par);
       tc_fence_after();
-      const uint32_t s_tmem = tmem_base + lane_base + (b ? Cfg::kColS1 : Cfg::kColS0);
+      const uint32_t s_tmem = tmem_base + lane_base + sb * 128;
       uint32_t sv[4][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
       tmem_ld_wait();
-      const int valid = p.nk - j * 128;  // keys valid in this tile (>= 1)
-      float mx = -INFINITY;
+      if constexpr (kMasked) {
+        const int valid = p.nk - j * 128;  // keys valid in this tile (>= 1)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
+      }
+      // row max: 8 independent chains
+      float mx8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx8[i] = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(sv[c][i]);
-          if (valid < 128 && (c * 32 + i) >= valid) s = -INFINITY;
-          sv[c][i] = __float_as_uint(s);
-          mx = fmaxf(mx, s);
-        }
+        for (int i = 0; i < 32; ++i) mx8[i & 7] = fmaxf(mx8[i & 7], __uint_as_float(sv[c][i]));
+      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                             fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       const float mt = mx * p.scale_log2;
       float alpha = 1.f;
       bool need = false;
@@ -217,56 +298,82 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         m_used = mt;
         need = true;
       }
-      float sum = 0.f;
-      uint32_t pk[2][32];
+      auto wait_and_rescale = [&]() {
+        // PV_{j-1} must have retired before P_j overwrites P_{j-1}/P_{j-2} and before the O row may be
+        // rescaled.  o_done phases are consumed strictly in order (one wait per tile): an mbarrier parity
+        // wait on a phase that has not started yet would return immediately.
+        if (j > 0) {
+          mbar_wait(od, (j - 1) & 1);
+          tc_fence_after();
+          if (__any_sync(0xffffffffu, need)) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 2 * NA; ++c) {
+              uint32_t ov[32];
+              tmem_ld32(o_tmem + c * 32, ov);
+              tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float e0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, -m_used));
-          float e1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, -m_used));
-          sum += e0 + e1;
-          pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
-        }
-      l_run = l_run * alpha + sum;
-      // PV_{j-1} must have retired before P_j overwrites the S/P buffer of tile j-2 and before the O
-      // row may be rescaled.  o_done phases are consumed strictly in order (one wait per tile): an
-      // mbarrier parity wait on a phase that has not started yet would return immediately.
-      if (j > 0) {
-        mbar_wait(o_done, (j - 1) & 1);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
-#pragma unroll
-          for (int c = 0; c < 2 * NA; ++c) {
-            uint32_t ov[32];
-            tmem_ld32(tmem_base + lane_base + Cfg::kColO + c * 32, ov);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
-            tmem_st32(tmem_base + lane_base + Cfg::kColO + c * 32, ov);
+              for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+              tmem_st32(o_tmem + c * 32, ov);
+            }
           }
         }
+      };
+      if constexpr (QT == 2) wait_and_rescale();  // already satisfied: QK_{j} was issued after PV_{j-1}
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      const float nm = -m_used;
+      if constexpr (QT == 2) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, nm));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, nm));
+            sum4[(i >> 1) & 3] += e0 + e1;
+            pk[i >> 1] = pack_bf16x2(e0, e1);
+          }
+          tmem_st16(s_tmem + c * 16, pk);
+        }
+      } else {
+        uint32_t pk[2][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, nm));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, nm));
+            sum4[(i >> 1) & 3] += e0 + e1;
+            pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
+          }
+        wait_and_rescale();  // late: the exps above overlap PV_{j-1}
+        tmem_st32(s_tmem, pk[0]);
+        tmem_st32(s_tmem + 32, pk[1]);
       }
-      tmem_st32(s_tmem, pk[0]);
-      tmem_st32(s_tmem + 32, pk[1]);
+      l_run = l_run * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
+      if (lane == 0) mbar_arrive(&p_full[sb]);
+    };
+    for (int j = 0; j + 1 < T; ++j) softmax_tile(j, std::false_type{});
+    if (p.nk % 128 != 0) {
+      softmax_tile(T - 1, std::true_type{});
+    } else {
+      softmax_tile(T - 1, std::false_type{});
     }
 
     // final: O / l  -> global (only the d valid channels of this head)
-    mbar_wait(o_done, (T - 1) & 1);
+    mbar_wait(&o_done[(QT == 2) ? tq : 0], (T - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
-    const int q = q0 + r;
+    const int q = q0 + 128 * tq + r;
     bf16* orow = p.o + static_cast<long long>(img) * p.o_stride_n + static_cast<long long>(q) * p.o_stride_t +
                  head * D;
 #pragma unroll
     for (int c = 0; c < 2 * NA; ++c) {
       if (c * 32 < D) {
         uint32_t ov[32];
-        tmem_ld32(tmem_base + lane_base + Cfg::kColO + c * 32, ov);
+        tmem_ld32(o_tmem + c * 32, ov);
         tmem_ld_wait();
         if (q < p.nq) {
 #pragma unroll
@@ -293,19 +400,29 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
   }
 }
 
-template <int D>
-static int launch_attn(const AttnKParams& kp, dim3 grid, cudaStream_t stream) {
-  using Cfg = AttnCfg<D>;
+template <int D, int QT>
+static int launch_attn(const AttnKParams& kp, int nq, int heads, int lanes, cudaStream_t stream) {
+  using Cfg = AttnCfg<D, QT>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<D, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  attn_kernel<D><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(kp);
+  dim3 grid((nq + 128 * QT - 1) / (128 * QT), heads, lanes);
+  attn_kernel<D, QT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();
   return static_cast<int>(cudaGetLastError());
+}
+
+// two query tiles per CTA whenever there are at least two (and the head dim leaves TMEM room)
+template <int D>
+static int launch_attn_auto(const AttnKParams& kp, int nq, int heads, int lanes, cudaStream_t stream) {
+  if constexpr (D <= 128) {
+    if (nq > 128) return launch_attn<D, 2>(kp, nq, heads, lanes, stream);
+  }
+  return launch_attn<D, 1>(kp, nq, heads, lanes, stream);
 }
 
 static int make_tok_map(CUtensorMap* m, const void* ptr, int channels, int tokens, int lanes, int64_t stride_t,
@@ -345,14 +462,14 @@ extern "C" int sg_attention(const sg_attn_args* a, void* stream_v) {
   kp.nk = a->nk;
   kp.n_heads = a->n_heads;
   kp.scale_log2 = a->scale * 1.4426950408889634f;
-  dim3 grid((a->nq + 127) / 128, a->n_heads, a->n_lanes);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int nq = a->nq, nh = a->n_heads, nl = a->n_lanes;
   switch (a->head_dim) {
-    case 32: return launch_attn<32>(kp, grid, stream);
-    case 40: return launch_attn<40>(kp, grid, stream);
-    case 64: return launch_attn<64>(kp, grid, stream);
-    case 80: return launch_attn<80>(kp, grid, stream);
-    case 128: return launch_attn<128>(kp, grid, stream);
-    default: return launch_attn<160>(kp, grid, stream);
+    case 32: return launch_attn_auto<32>(kp, nq, nh, nl, stream);
+    case 40: return launch_attn_auto<40>(kp, nq, nh, nl, stream);
+    case 64: return launch_attn_auto<64>(kp, nq, nh, nl, stream);
+    case 80: return launch_attn_auto<80>(kp, nq, nh, nl, stream);
+    case 128: return launch_attn_auto<128>(kp, nq, nh, nl, stream);
+    default: return launch_attn_auto<160>(kp, nq, nh, nl, stream);
   }
 }

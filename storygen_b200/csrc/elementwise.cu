@@ -219,34 +219,59 @@ __global__ void timestep_features_kernel(const float* __restrict__ t, int n, int
   out[r * dim + half + i] = sinf(arg);
 }
 
-// out[r][m] = act_out( sum_k W[m][k] * act_in(x[r][k]) + b[m] ); one warp per output feature m.
+// out[r][m] = act_out( sum_k W[m][k] * act_in(x[r][k]) + b[m] ); one warp per kF consecutive output
+// features: the warp keeps its kF weight rows in registers (k <= 1280) and streams the n activation rows
+// once, so activations are re-read m/kF times instead of m times.
+constexpr int kSlF = 4;     // features per warp
+constexpr int kSlMaxV = 5;  // 16-byte weight vectors per lane per feature (k <= 32*8*5 = 1280)
 __global__ void small_linear_kernel(const float* __restrict__ x, int n, int k, const bf16* __restrict__ w,
                                     const float* __restrict__ b, int m, int silu_in, int silu_out,
                                     float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= m) return;
-  const bf16* wr = w + static_cast<long long>(row) * k;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kSlF;
+  if (row0 >= m) return;
   const int V = k / 8;
-  for (int r = 0; r < n; ++r) {
-    float acc = 0.f;
-    for (int v = lane; v < V; v += 32) {
-      float wf[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(wr + v * 8)), wf);
-      const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r) * k + v * 8));
-      const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r) * k + v * 8 + 4));
-      float xf[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  float wf[kSlF][kSlMaxV][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xv = silu_in ? silu_f(xf[i]) : xf[i];
-        acc = fmaf(wf[i], xv, acc);
+  for (int f = 0; f < kSlF; ++f)
+#pragma unroll
+    for (int i = 0; i < kSlMaxV; ++i) {
+      const int v = lane + 32 * i;
+      if (row0 + f < m && v < V) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(w + static_cast<long long>(row0 + f) * k + v * 8)), wf[f][i]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) wf[f][i][e] = 0.f;
+      }
+    }
+  for (int r = 0; r < n; ++r) {
+    float acc[kSlF];
+#pragma unroll
+    for (int f = 0; f < kSlF; ++f) acc[f] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSlMaxV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < V) {
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r) * k + v * 8));
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r) * k + v * 8 + 4));
+        float xf[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xv = silu_in ? silu_f(xf[e]) : xf[e];
+#pragma unroll
+          for (int f = 0; f < kSlF; ++f) acc[f] = fmaf(wf[f][i][e], xv, acc[f]);
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-      float y = acc + (b ? b[row] : 0.f);
-      out[static_cast<long long>(r) * m + row] = silu_out ? silu_f(y) : y;
+    for (int f = 0; f < kSlF; ++f) {
+      float a = acc[f];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0 && row0 + f < m) {
+        const float y = a + (b ? b[row0 + f] : 0.f);
+        out[static_cast<long long>(r) * m + row0 + f] = silu_out ? silu_f(y) : y;
+      }
     }
   }
 }
@@ -395,8 +420,9 @@ extern "C" int sg_timestep_features(const float* t, int32_t n, int32_t dim, floa
 extern "C" int sg_small_linear(const float* x, int32_t n, int32_t k, const void* w, const float* b, int32_t m,
                                int32_t silu_in, int32_t silu_out, float* out, void* stream) {
   if (!x || !w || !out) return SG_ERR_ARG;
-  if (k % 8) return SG_ERR_SHAPE;
-  small_linear_kernel<<<(m + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (k % 8 || k > 32 * 8 * kSlMaxV) return SG_ERR_SHAPE;
+  const int warps_needed = (m + kSlF - 1) / kSlF;
+  small_linear_kernel<<<(warps_needed + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       x, n, k, static_cast<const bf16*>(w), b, m, silu_in, silu_out, out);
   SG_LAUNCH_END();
 }

@@ -4,7 +4,11 @@
 //                                B = pre-packed weights), kStages-deep smem ring
 //   warp 1      : MMA issuer    (one elected lane; tcgen05.mma M=128 x N=BN x K=16, fp32 in TMEM,
 //                                two accumulator stages so the epilogue of tile i overlaps tile i+1)
-//   warps 2..5  : epilogue      (tcgen05.ld -> bias / time-embedding / residual / GEGLU -> bf16 stores)
+//   warps 2..9  : epilogue      two warpgroups, each thread owns one accumulator row; the 32-column chunks
+//                               of a tile alternate between the groups (2 warps per SM sub-partition hide
+//                               each other's TMEM / global latency); residual row segments are prefetched
+//                               into registers before the accumulator is awaited
+//                               (tcgen05.ld -> bias / time-embedding / residual / GEGLU -> bf16 stores)
 //
 // Tile = 128 output pixels (a bw x bh x bn box of the NHWC output grid) x BN output channels.
 // K loop = list of segments (source tensor, dx, dy, first channel, #64-channel blocks): this one
@@ -16,7 +20,8 @@ namespace sg {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // one 128-byte swizzle atom of bf16
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 2 epilogue warpgroups
+constexpr int kEpiWarps = 8;
 
 struct GemmKParams {
   CUtensorMap a_maps[SG_MAX_SRC];
@@ -51,11 +56,21 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// erf-GELU with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 output rounding):
+// 2 MUFU + ~10 FMA instead of the ~35-instruction erff(), which made the GEGLU epilogue the bottleneck.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * fast_exp2(-1.4426950408889634f * z * z);
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
 }
 
-template <int BN>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_kernel(const __grid_constant__ GemmKParams p) {
   using Cfg = GemmCfg<BN>;
@@ -84,7 +99,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -165,11 +180,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
   } else {
     // ===================== epilogue =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;       // epilogue warpgroup 0 / 1: chunks c = grp, grp + 2, ...
     const int r = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool geglu = (p.mode == SG_EPI_GEGLU);
+    constexpr int kChunks = BN / 32;
+    constexpr int kMine = (kChunks + 1) / 2;  // chunks per warpgroup (<= 4)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.num_n_tiles;
       const int nt = tile - mt * p.num_n_tiles;
@@ -182,94 +199,121 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const bool row_ok = (x < p.out_w) && (y < p.out_h) && (n < p.out_n);
       const long long m = (static_cast<long long>(n) * p.out_h + y) * p.out_w + x;
 
+      // Residual prefetch: this thread's row segments go to registers BEFORE the accumulator is awaited,
+      // so their DRAM latency overlaps the tile's main loop (one latency per tile, not one per chunk).
+      uint4 res[kMine * 4];
+      const bool use_res = (MODE == SG_EPI_LINEAR) && (p.residual != nullptr) && row_ok;
+      if constexpr (MODE == SG_EPI_LINEAR) {
+        if (use_res) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + nt * BN);
+#pragma unroll
+          for (int i = 0; i < kMine; ++i) {
+            const int c = grp + 2 * i;
+            if (c < kChunks && nt * BN + c * 32 < p.N) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) res[i * 4 + j] = __ldg(r4 + c * 4 + j);
+            }
+          }
+        }
+      }
+      const float* lane_bias_row =
+          (p.lane_bias != nullptr) ? p.lane_bias + static_cast<long long>(n) * p.ld_lane_bias : nullptr;
+
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_row + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = nt * BN + c * 32;
-        if (col0 < p.N && row_ok) {
-          float f[32];
+      // double-buffered TMEM loads, except where the residual prefetch already fills the register file
+      constexpr bool kDouble = !(MODE == SG_EPI_LINEAR && BN == 256);
+      uint32_t v[kDouble ? 2 : 1][32];
+      if (kDouble && grp < kChunks) tmem_ld32(t_row + grp * 32, v[0]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+      for (int i = 0; i < kMine; ++i) {
+        const int c = grp + 2 * i;
+        if (c < kChunks) {  // warp-uniform
+          if constexpr (!kDouble) tmem_ld32(t_row + c * 32, v[0]);
+          tmem_ld_wait();
+          if (kDouble && i + 1 < kMine && c + 2 < kChunks)
+            tmem_ld32(t_row + (c + 2) * 32, v[(i + 1) & 1]);  // overlaps the math below
+          const int col0 = nt * BN + c * 32;
+          if (col0 < p.N && row_ok) {
+            float f[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 b = __ldg(b4 + j);
-              f[4 * j + 0] += b.x;
-              f[4 * j + 1] += b.y;
-              f[4 * j + 2] += b.z;
-              f[4 * j + 3] += b.w;
-            }
-          }
-          if (p.lane_bias != nullptr) {
-            const float4* b4 =
-                reinterpret_cast<const float4*>(p.lane_bias + static_cast<long long>(n) * p.ld_lane_bias + col0);
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[kDouble ? (i & 1) : 0][j]);
+            if (p.bias != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 b = __ldg(b4 + j);
-              f[4 * j + 0] += b.x;
-              f[4 * j + 1] += b.y;
-              f[4 * j + 2] += b.z;
-              f[4 * j + 3] += b.w;
-            }
-          }
-          if (p.mode == SG_EPI_NCHW_F32) {
-            // final conv: fp32 NCHW store of the first out_channels columns (coalesced along x)
-            if (c == 0) {
-              float* of = reinterpret_cast<float*>(p.out);
-              const long long plane = static_cast<long long>(p.out_h) * p.out_w;
-              const long long base = static_cast<long long>(n) * p.out_channels * plane + static_cast<long long>(y) * p.out_w + x;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < p.out_channels) of[base + j * plane] = f[j];
-            }
-          } else if (!geglu) {
-            if (p.residual != nullptr) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 q = __ldg(r4 + j);
-                float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), cc = unpack_bf16x2(q.z),
-                       d = unpack_bf16x2(q.w);
-                f[8 * j + 0] += p.res_scale * a.x;
-                f[8 * j + 1] += p.res_scale * a.y;
-                f[8 * j + 2] += p.res_scale * b.x;
-                f[8 * j + 3] += p.res_scale * b.y;
-                f[8 * j + 4] += p.res_scale * cc.x;
-                f[8 * j + 5] += p.res_scale * cc.y;
-                f[8 * j + 6] += p.res_scale * d.x;
-                f[8 * j + 7] += p.res_scale * d.y;
+              for (int j = 0; j < 8; ++j) {
+                float4 bb = __ldg(b4 + j);
+                f[4 * j + 0] += bb.x;
+                f[4 * j + 1] += bb.y;
+                f[4 * j + 2] += bb.z;
+                f[4 * j + 3] += bb.w;
               }
             }
-            uint4* o4 = reinterpret_cast<uint4*>(p.out + m * p.ldo + col0);
+            if (lane_bias_row != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(lane_bias_row + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 q;
-              q.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              o4[j] = q;
+              for (int j = 0; j < 8; ++j) {
+                float4 bb = __ldg(b4 + j);
+                f[4 * j + 0] += bb.x;
+                f[4 * j + 1] += bb.y;
+                f[4 * j + 2] += bb.z;
+                f[4 * j + 3] += bb.w;
+              }
             }
-          } else {
-            // columns [0,16) = value, [16,32) = gate (weights pre-interleaved on the host)
-            float g[16];
+            if constexpr (MODE == SG_EPI_NCHW_F32) {
+              // final conv: fp32 NCHW store of the first out_channels columns (coalesced along x)
+              if (c == 0) {
+                float* of = reinterpret_cast<float*>(p.out);
+                const long long plane = static_cast<long long>(p.out_h) * p.out_w;
+                const long long base =
+                    static_cast<long long>(n) * p.out_channels * plane + static_cast<long long>(y) * p.out_w + x;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) g[j] = f[j] * gelu_erf(f[16 + j]);
-            uint4* o4 = reinterpret_cast<uint4*>(p.out + m * p.ldo + (col0 >> 1));
+                for (int j = 0; j < 32; ++j)
+                  if (j < p.out_channels) of[base + j * plane] = f[j];
+              }
+            } else if constexpr (MODE == SG_EPI_LINEAR) {
+              if (use_res) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint4 q;
-              q.x = pack_bf16x2(g[8 * j + 0], g[8 * j + 1]);
-              q.y = pack_bf16x2(g[8 * j + 2], g[8 * j + 3]);
-              q.z = pack_bf16x2(g[8 * j + 4], g[8 * j + 5]);
-              q.w = pack_bf16x2(g[8 * j + 6], g[8 * j + 7]);
-              o4[j] = q;
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 q = res[i * 4 + j];
+                  float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), cc = unpack_bf16x2(q.z),
+                         d = unpack_bf16x2(q.w);
+                  f[8 * j + 0] = fmaf(p.res_scale, a.x, f[8 * j + 0]);
+                  f[8 * j + 1] = fmaf(p.res_scale, a.y, f[8 * j + 1]);
+                  f[8 * j + 2] = fmaf(p.res_scale, b.x, f[8 * j + 2]);
+                  f[8 * j + 3] = fmaf(p.res_scale, b.y, f[8 * j + 3]);
+                  f[8 * j + 4] = fmaf(p.res_scale, cc.x, f[8 * j + 4]);
+                  f[8 * j + 5] = fmaf(p.res_scale, cc.y, f[8 * j + 5]);
+                  f[8 * j + 6] = fmaf(p.res_scale, d.x, f[8 * j + 6]);
+                  f[8 * j + 7] = fmaf(p.res_scale, d.y, f[8 * j + 7]);
+                }
+              }
+              uint4* o4 = reinterpret_cast<uint4*>(p.out + m * p.ldo + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 q;
+                q.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                o4[j] = q;
+              }
+            } else {
+              // GEGLU: columns [0,16) = value, [16,32) = gate (weights pre-interleaved on the host)
+              float g[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) g[j] = f[j] * gelu_erf(f[16 + j]);
+              uint4* o4 = reinterpret_cast<uint4*>(p.out + m * p.ldo + (col0 >> 1));
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                uint4 q;
+                q.x = pack_bf16x2(g[8 * j + 0], g[8 * j + 1]);
+                q.y = pack_bf16x2(g[8 * j + 2], g[8 * j + 3]);
+                q.z = pack_bf16x2(g[8 * j + 4], g[8 * j + 5]);
+                q.w = pack_bf16x2(g[8 * j + 6], g[8 * j + 7]);
+                o4[j] = q;
+              }
             }
           }
         }
@@ -292,20 +336,31 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
 }
 
-template <int BN>
-static int launch_gemm(const GemmKParams& kp, int num_tiles, cudaStream_t stream) {
+template <int BN, int MODE>
+static int launch_gemm_mode(const GemmKParams& kp, int num_tiles, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
   int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
+  gemm_kernel<BN, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();
   return static_cast<int>(cudaGetLastError());
+}
+
+template <int BN>
+static int launch_gemm(const GemmKParams& kp, int num_tiles, cudaStream_t stream) {
+  switch (kp.mode) {
+    case SG_EPI_GEGLU: return launch_gemm_mode<BN, SG_EPI_GEGLU>(kp, num_tiles, stream);
+    case SG_EPI_NCHW_F32:
+      if constexpr (BN == 64) return launch_gemm_mode<BN, SG_EPI_NCHW_F32>(kp, num_tiles, stream);
+      return SG_ERR_SHAPE;
+    default: return launch_gemm_mode<BN, SG_EPI_LINEAR>(kp, num_tiles, stream);
+  }
 }
 
 }  // namespace sg
