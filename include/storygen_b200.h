@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 5
+#define SG_ABI_VERSION 6
 
 #define SG_ERR_SHAPE (-1)   /* unsupported / inconsistent shape            */
 #define SG_ERR_ALIGN (-2)   /* pointer or stride not 16-byte aligned        */
@@ -126,6 +126,7 @@ typedef struct sg_attn_args {
   int32_t n_kv_lanes;    /* number of K/V lanes (0 = n_lanes)                                  */
   const int32_t* kv_map; /* optional device int32[n_lanes]: K/V lane of each Q lane; NULL = identity */
   float scale;        /* softmax scale (head_dim^-0.5)                                        */
+  int64_t* debug_timeline; /* bring-up aid: device int64[12*16*8] phase clocks of CTA 0, or NULL     */
 } sg_attn_args;
 
 int sg_attention(const sg_attn_args* args, void* stream);

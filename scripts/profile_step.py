@@ -25,8 +25,13 @@ loop.par.copy_(loop.tab[0]); loop.par_i.copy_(loop.tab_i[0])
 with torch.no_grad():
     loop._step_body()  # warm-up
     torch.cuda.synchronize()
+    from storygen_b200 import ops
+    ops.TRACE = []
     torch.cuda.profiler.start()
     loop._step_body()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
+    import json
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(ops.TRACE, open("gpurun_out/trace_step.json", "w"))
 print("profiled one denoising step: B=%d R=%d" % (B, R))

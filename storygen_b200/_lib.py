@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstorygen_b200.so")
 
-SG_ABI_VERSION = 5
+SG_ABI_VERSION = 6
 SG_MAX_SRC = 4
 SG_MAX_SEGS = 24
 SG_EPI_LINEAR = 0
@@ -50,7 +50,8 @@ class SgAttnArgs(C.Structure):
                 ("k_stride_t", C.c_int64), ("v_stride_n", C.c_int64), ("v_stride_t", C.c_int64),
                 ("o_stride_n", C.c_int64), ("o_stride_t", C.c_int64), ("n_lanes", C.c_int32),
                 ("n_heads", C.c_int32), ("head_dim", C.c_int32), ("nq", C.c_int32), ("nk", C.c_int32),
-                ("n_kv_lanes", C.c_int32), ("kv_map", C.c_void_p), ("scale", C.c_float)]
+                ("n_kv_lanes", C.c_int32), ("kv_map", C.c_void_p), ("scale", C.c_float),
+                ("debug_timeline", C.c_void_p)]
 
 
 class LibraryError(RuntimeError):

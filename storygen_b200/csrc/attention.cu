@@ -29,6 +29,7 @@ struct AttnKParams {
   bf16* o;
   long long o_stride_n, o_stride_t;
   const int* kv_map;
+  long long* dbg;  // optional phase timestamps of CTA (0,0,0): [warp][tile][8] (bring-up aid, NULL in production)
   int nq, nk, n_heads;
   float scale_log2;  // scale * log2(e)
 };
@@ -46,10 +47,21 @@ struct AttnCfg {
   static constexpr int kFirstSoftmaxWarp = (QT == 2) ? 4 : 2;  // QT == 2: warpgroup 0 = {TMA, MMA, 2 idle}
   static constexpr int kThreads = 32 * kFirstSoftmaxWarp + 128 * QT;
   static constexpr int kSmemBytes = kTileBytes * (QT + kSlots) + 1024 + 256;
-  static constexpr int kColO = 256;
+  // kSepP (two query tiles, one 64-channel atom): P gets its own TMEM columns instead of aliasing S, so the
+  // tensor core may overwrite S_t with Q K_{j+1}^T as soon as the softmax warps have READ S_t(j) -- the
+  // PV_j -> QK_{j+1} -> commit -> wake-up round trip (~1200 clk measured) leaves the softmax critical path.
+  //   columns: S_t at t*128 | P_t at 256 + t*64 | O_t at 384 + t*64
+  static constexpr bool kSepP = (QT == 2 && NA == 1);
+  static constexpr int kColP = 256;
+  static constexpr int kColO = kSepP ? 384 : 256;
   static constexpr int kTmemCols = 512;
   static_assert(QT == 1 || NA <= 2, "two query tiles need 2 x 64*NA O columns next to 256 S columns");
 };
+
+#define SG_TS(slot)                                                                                   \
+  do {                                                                                                \
+    if (dbg_on && lane == 0 && j < 16) p.dbg[(warp * 16 + j) * 8 + (slot)] = clock64();               \
+  } while (0)
 
 template <int D, int QT>
 __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
@@ -69,7 +81,8 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
   uint64_t* s_full = q_ready + 2;        // [2] MMA -> softmax
   uint64_t* p_full = s_full + 2;         // [2] softmax -> MMA
   uint64_t* o_done = p_full + 2;         // [2] MMA -> softmax (PV retired)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_free = o_done + 2;         // [2] softmax -> MMA (S row-blocks are in registers; kSepP only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -77,6 +90,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
   const int head = blockIdx.y;
   const int img = blockIdx.z;
   const int T = (p.nk + 127) / 128;
+  const bool dbg_on = (p.dbg != nullptr) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSlots; ++i) {
@@ -89,6 +103,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&o_done[i], 1);
+      mbar_init(&s_free[i], 4);
     }
     fence_barrier_init();
   }
@@ -198,7 +213,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
             phase ^= 1;
           }
         }
-      } else {
+      } else if constexpr (!Cfg::kSepP) {
         auto slot_of = [](int i) { return i % kSlots; };
         auto phase_of = [](int i) { return static_cast<uint32_t>((i / kSlots) & 1); };
         auto tile_addr = [&](int i) { return smem_u32(kv_smem + slot_of(i) * Cfg::kTileBytes); };
@@ -230,6 +245,53 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
           umma_commit(&kv_empty[slot_of(iv)]);
           if (more) umma_commit(&kv_empty[slot_of(ik)]);
         }
+      } else {
+        // Event-driven issue (kSepP): per query tile t two independent streams,
+        //   QK_t(j) as soon as K_j has landed and the softmax warps have read S_t(j-1)   [s_free]
+        //   PV_t(j) as soon as V_j has landed and P_t(j) is published                    [p_full]
+        // polled round-robin with non-blocking mbarrier tests.  Every barrier phase is tested only after
+        // the previous phase of that barrier was seen complete (parity waits are only valid in order).
+        auto slot_of = [](int i) { return i % kSlots; };
+        auto phase_of = [](int i) { return static_cast<uint32_t>((i / kSlots) & 1); };
+        auto tile_addr = [&](int i) { return smem_u32(kv_smem + slot_of(i) * Cfg::kTileBytes); };
+        int qk_next[2] = {0, 0}, pv_next[2] = {0, 0};
+        uint32_t spins = 0;
+        while (pv_next[0] < T || pv_next[1] < T) {
+          bool progress = false;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (qk_next[t] < T) {
+              const int j = qk_next[t], ik = 2 * j;
+              const bool s_ok = (j == 0) ? mbar_test(&q_ready[t], 0) : mbar_test(&s_free[t], (j - 1) & 1);
+              if (s_ok && mbar_test(&kv_full[slot_of(ik)], phase_of(ik))) {
+                tc_fence_after();
+                if (dbg_on && j < 16) p.dbg[(1 * 16 + j) * 8 + t * 2] = clock64();
+                qk(smem_u32(q_smem + t * Cfg::kTileBytes), tile_addr(ik), t * 128);
+                umma_commit(&s_full[t]);
+                qk_next[t] = j + 1;
+                if (qk_next[1 - t] > j) umma_commit(&kv_empty[slot_of(ik)]);  // both tiles have used K_j
+                progress = true;
+              }
+            }
+            if (pv_next[t] < T) {
+              const int j = pv_next[t], iv = 2 * j + 1;
+              if (mbar_test(&p_full[t], j & 1) && mbar_test(&kv_full[slot_of(iv)], phase_of(iv))) {
+                tc_fence_after();
+                if (dbg_on && j < 16) p.dbg[(1 * 16 + j) * 8 + t * 2 + 1] = clock64();
+                pv(Cfg::kColP + t * 64, tile_addr(iv), Cfg::kColO + t * 64, j == 0);
+                umma_commit(&o_done[t]);
+                pv_next[t] = j + 1;
+                if (pv_next[1 - t] > j) umma_commit(&kv_empty[slot_of(iv)]);  // both tiles have used V_j
+                progress = true;
+              }
+            }
+          }
+          if (progress) {
+            spins = 0;
+          } else if (++spins > (1u << 24)) {
+            __trap();  // lost arrive: fail loudly instead of hanging
+          }
+        }
       }
     }
   }
@@ -256,6 +318,9 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
     if (lane == 0) mbar_arrive(&q_ready[tq]);
 
     float m_used = 0.f, l_run = 0.f;
+    if constexpr (QT == 2) {
+      if (tq == 1) named_bar_arrive(1, 256);  // warpgroup 0 owns the exp unit first
+    }
     // one KV tile of the online softmax; kMasked is only instantiated for the LAST tile (ragged nk), so the
     // 128-element mask (ISETP + SEL per element once if-converted) stays out of the steady-state loop
     auto softmax_tile = [&](const int j, auto masked_tag) {
@@ -263,13 +328,22 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
       const int sb = (QT == 2) ? tq : (j & 1);                         // S / P buffer
       const uint32_t s_par = (QT == 2) ? (j & 1) : ((j >> 1) & 1);
       uint64_t* od = &o_done[(QT == 2) ? tq : 0];
+      SG_TS(0);
       mbar_wait(&s_full[sb], s_par);
       tc_fence_after();
+      SG_TS(1);
       const uint32_t s_tmem = tmem_base + lane_base + sb * 128;
       uint32_t sv[4][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
       tmem_ld_wait();
+      if constexpr (Cfg::kSepP) {
+        // S_t(j) is in registers: the tensor core may overwrite it with Q_t K_{j+1}^T
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[tq]);
+      }
+      SG_TS(2);
       if constexpr (kMasked) {
         const int valid = p.nk - j * 128;  // keys valid in this tile (>= 1)
 #pragma unroll
@@ -322,6 +396,13 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       const float nm = -m_used;
       if constexpr (QT == 2) {
+        // Warpgroup ping-pong on the MUFU pipe: the two softmax warpgroups share each sub-partition's
+        // 4-lane/clk exp unit.  Left alone they fall into lockstep (both in the exp phase, then both idle
+        // behind the MMA chain); with the exp phase made exclusive, one group's TMEM load / row max / P store
+        // / wait for the tensor core overlaps the other group's exps.  Barrier 1 + t admits warpgroup t.
+        SG_TS(3);
+        named_bar_sync(1 + tq, 256);
+        SG_TS(4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
@@ -332,8 +413,11 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
             sum4[(i >> 1) & 3] += e0 + e1;
             pk[i >> 1] = pack_bf16x2(e0, e1);
           }
-          tmem_st16(s_tmem + c * 16, pk);
+          tmem_st16((Cfg::kSepP ? (tmem_base + lane_base + Cfg::kColP + tq * 64) : s_tmem) + c * 16, pk);
         }
+        // hand the exp unit to the other warpgroup (its tile j if we are group 0, tile j+1 if we are group 1)
+        SG_TS(5);
+        if (!(tq == 1 && j == T - 1)) named_bar_arrive(2 - tq, 256);
       } else {
         uint32_t pk[2][32];
 #pragma unroll
@@ -354,6 +438,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
+      SG_TS(6);
     };
     for (int j = 0; j + 1 < T; ++j) softmax_tile(j, std::false_type{});
     if (p.nk % 128 != 0) {
@@ -458,6 +543,7 @@ extern "C" int sg_attention(const sg_attn_args* a, void* stream_v) {
   kp.o_stride_n = a->o_stride_n;
   kp.o_stride_t = a->o_stride_t;
   kp.kv_map = a->kv_map;
+  kp.dbg = reinterpret_cast<long long*>(a->debug_timeline);
   kp.nq = a->nq;
   kp.nk = a->nk;
   kp.n_heads = a->n_heads;

@@ -50,15 +50,23 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x0, int c0, const bf16*
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  for (int p = p_begin + pl; p < p_end; p += PS) {
-    uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p) * cs));
-    float f[8];
-    unpack8(raw, f);
+  // 4 independent 16-byte loads in flight per thread (memory-level parallelism), then the arithmetic
+  for (int p = p_begin + pl; p < p_end; p += 4 * PS) {
+    uint4 raw[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s[i] += f[i];
-      q[i] += f[i] * f[i];
-    }
+    for (int u = 0; u < 4; ++u)
+      if (p + u * PS < p_end) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p + u * PS) * cs));
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (p + u * PS < p_end) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          q[i] += f[i] * f[i];
+        }
+      }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -120,16 +128,23 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x0, int c0, const bf16*
     b[i] = beta[c] - s_mean[g] * ga;
   }
   bf16* ybase = y + static_cast<long long>(n) * hw * C + v * 8;
-  for (int p = p_begin + pl; p < p_end; p += PS) {
-    uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p) * cs));
-    float f[8];
-    unpack8(raw, f);
+  for (int p = p_begin + pl; p < p_end; p += 4 * PS) {
+    uint4 raw[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float t = fmaf(f[i], a[i], b[i]);
-      f[i] = silu ? silu_f(t) : t;
-    }
-    *reinterpret_cast<uint4*>(ybase + static_cast<long long>(p) * C) = pack8(f);
+    for (int u = 0; u < 4; ++u)
+      if (p + u * PS < p_end) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p + u * PS) * cs));
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (p + u * PS < p_end) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float t = fmaf(f[i], a[i], b[i]);
+          f[i] = silu ? silu_f(t) : t;
+        }
+        *reinterpret_cast<uint4*>(ybase + static_cast<long long>(p + u * PS) * C) = pack8(f);
+      }
   }
 }
 

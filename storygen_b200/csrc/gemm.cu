@@ -14,61 +14,9 @@
 // K loop = list of segments (source tensor, dx, dy, first channel, #64-channel blocks): this one
 // kernel is Linear, 1x1 conv, 3x3 conv (stride 1 or, via phase-strided sources, stride 2), conv over
 // a channel-concat of two tensors, and conv + fused 1x1 shortcut.  See include/storygen_b200.h.
-#include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace sg {
-
-constexpr int kBM = 128;
-constexpr int kBK = 64;  // one 128-byte swizzle atom of bf16
-constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 2 epilogue warpgroups
-constexpr int kEpiWarps = 8;
-
-struct GemmKParams {
-  CUtensorMap a_maps[SG_MAX_SRC];
-  CUtensorMap b_map;
-  sg_seg segs[SG_MAX_SEGS];
-  int num_segs;
-  int total_kb;
-  int out_w, out_h, out_n;
-  int bw, bh, bn;
-  int tiles_x, tiles_y, tiles_n;  // M tiles = tiles_x * tiles_y * tiles_n
-  int num_n_tiles;
-  int N;
-  int mode;
-  int out_channels;  // SG_EPI_NCHW_F32: number of valid output channels (<= 32)
-  float res_scale;
-  const float* bias;
-  const float* lane_bias;
-  long long ld_lane_bias;
-  const bf16* residual;
-  long long ldr;
-  bf16* out;
-  long long ldo;
-};
-
-template <int BN>
-struct GemmCfg {
-  static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
-  static constexpr int kBBytes = BN * kBK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-};
-
-// erf-GELU with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 output rounding):
-// 2 MUFU + ~10 FMA instead of the ~35-instruction erff(), which made the GEGLU epilogue the bottleneck.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erf_abs = 1.0f - poly * t * fast_exp2(-1.4426950408889634f * z * z);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
-}
 
 template <int BN, int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -80,7 +28,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* epi_scratch = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_scratch + Cfg::kScratchBytes);
   uint64_t* full_bar = bars;                      // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;      // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;  // [2]
@@ -179,145 +128,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       }
     }
   } else {
-    // ===================== epilogue =====================
-    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int grp = (warp - 2) >> 2;       // epilogue warpgroup 0 / 1: chunks c = grp, grp + 2, ...
-    const int r = quarter * 32 + lane;
+    // ===================== epilogue (see gemm_common.cuh::epilogue_tile) =====================
+    const int quarter = warp & 3;     // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;  // epilogue warpgroup 0 / 1
+    uint8_t* scratch = epi_scratch + (warp - 2) * 4096;
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr int kChunks = BN / 32;
-    constexpr int kMine = (kChunks + 1) / 2;  // chunks per warpgroup (<= 4)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.num_n_tiles;
       const int nt = tile - mt * p.num_n_tiles;
-      const int tx = mt % p.tiles_x;
-      const int ty = (mt / p.tiles_x) % p.tiles_y;
-      const int tn = mt / (p.tiles_x * p.tiles_y);
-      const int x = tx * p.bw + r % p.bw;
-      const int y = ty * p.bh + (r / p.bw) % p.bh;
-      const int n = tn * p.bn + r / (p.bw * p.bh);
-      const bool row_ok = (x < p.out_w) && (y < p.out_h) && (n < p.out_n);
-      const long long m = (static_cast<long long>(n) * p.out_h + y) * p.out_w + x;
-
-      // Residual prefetch: this thread's row segments go to registers BEFORE the accumulator is awaited,
-      // so their DRAM latency overlaps the tile's main loop (one latency per tile, not one per chunk).
-      uint4 res[kMine * 4];
-      const bool use_res = (MODE == SG_EPI_LINEAR) && (p.residual != nullptr) && row_ok;
-      if constexpr (MODE == SG_EPI_LINEAR) {
-        if (use_res) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + m * p.ldr + nt * BN);
-#pragma unroll
-          for (int i = 0; i < kMine; ++i) {
-            const int c = grp + 2 * i;
-            if (c < kChunks && nt * BN + c * 32 < p.N) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) res[i * 4 + j] = __ldg(r4 + c * 4 + j);
-            }
-          }
-        }
-      }
-      const float* lane_bias_row =
-          (p.lane_bias != nullptr) ? p.lane_bias + static_cast<long long>(n) * p.ld_lane_bias : nullptr;
-
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      // double-buffered TMEM loads, except where the residual prefetch already fills the register file
-      constexpr bool kDouble = !(MODE == SG_EPI_LINEAR && BN == 256);
-      uint32_t v[kDouble ? 2 : 1][32];
-      if (kDouble && grp < kChunks) tmem_ld32(t_row + grp * 32, v[0]);
-#pragma unroll
-      for (int i = 0; i < kMine; ++i) {
-        const int c = grp + 2 * i;
-        if (c < kChunks) {  // warp-uniform
-          if constexpr (!kDouble) tmem_ld32(t_row + c * 32, v[0]);
-          tmem_ld_wait();
-          if (kDouble && i + 1 < kMine && c + 2 < kChunks)
-            tmem_ld32(t_row + (c + 2) * 32, v[(i + 1) & 1]);  // overlaps the math below
-          const int col0 = nt * BN + c * 32;
-          if (col0 < p.N && row_ok) {
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[kDouble ? (i & 1) : 0][j]);
-            if (p.bias != nullptr) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 bb = __ldg(b4 + j);
-                f[4 * j + 0] += bb.x;
-                f[4 * j + 1] += bb.y;
-                f[4 * j + 2] += bb.z;
-                f[4 * j + 3] += bb.w;
-              }
-            }
-            if (lane_bias_row != nullptr) {
-              const float4* b4 = reinterpret_cast<const float4*>(lane_bias_row + col0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 bb = __ldg(b4 + j);
-                f[4 * j + 0] += bb.x;
-                f[4 * j + 1] += bb.y;
-                f[4 * j + 2] += bb.z;
-                f[4 * j + 3] += bb.w;
-              }
-            }
-            if constexpr (MODE == SG_EPI_NCHW_F32) {
-              // final conv: fp32 NCHW store of the first out_channels columns (coalesced along x)
-              if (c == 0) {
-                float* of = reinterpret_cast<float*>(p.out);
-                const long long plane = static_cast<long long>(p.out_h) * p.out_w;
-                const long long base =
-                    static_cast<long long>(n) * p.out_channels * plane + static_cast<long long>(y) * p.out_w + x;
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < p.out_channels) of[base + j * plane] = f[j];
-              }
-            } else if constexpr (MODE == SG_EPI_LINEAR) {
-              if (use_res) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint4 q = res[i * 4 + j];
-                  float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), cc = unpack_bf16x2(q.z),
-                         d = unpack_bf16x2(q.w);
-                  f[8 * j + 0] = fmaf(p.res_scale, a.x, f[8 * j + 0]);
-                  f[8 * j + 1] = fmaf(p.res_scale, a.y, f[8 * j + 1]);
-                  f[8 * j + 2] = fmaf(p.res_scale, b.x, f[8 * j + 2]);
-                  f[8 * j + 3] = fmaf(p.res_scale, b.y, f[8 * j + 3]);
-                  f[8 * j + 4] = fmaf(p.res_scale, cc.x, f[8 * j + 4]);
-                  f[8 * j + 5] = fmaf(p.res_scale, cc.y, f[8 * j + 5]);
-                  f[8 * j + 6] = fmaf(p.res_scale, d.x, f[8 * j + 6]);
-                  f[8 * j + 7] = fmaf(p.res_scale, d.y, f[8 * j + 7]);
-                }
-              }
-              uint4* o4 = reinterpret_cast<uint4*>(p.out + m * p.ldo + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 q;
-                q.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-                o4[j] = q;
-              }
-            } else {
-              // GEGLU: columns [0,16) = value, [16,32) = gate (weights pre-interleaved on the host)
-              float g[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) g[j] = f[j] * gelu_erf(f[16 + j]);
-              uint4* o4 = reinterpret_cast<uint4*>(p.out + m * p.ldo + (col0 >> 1));
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                uint4 q;
-                q.x = pack_bf16x2(g[8 * j + 0], g[8 * j + 1]);
-                q.y = pack_bf16x2(g[8 * j + 2], g[8 * j + 3]);
-                q.z = pack_bf16x2(g[8 * j + 4], g[8 * j + 5]);
-                q.w = pack_bf16x2(g[8 * j + 6], g[8 * j + 7]);
-                o4[j] = q;
-              }
-            }
-          }
-        }
-      }
+      epilogue_tile<BN, MODE>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -426,6 +247,7 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   kp.num_n_tiles = static_cast<int>((a->N + bn_tile - 1) / bn_tile);
   kp.N = static_cast<int>(a->N);
   kp.mode = a->mode;
+  kp.transpose_epi = (a->mode != SG_EPI_LINEAR) || (total_kb <= 24);
   kp.out_channels = a->out_channels;
   kp.res_scale = a->res_scale;
   kp.bias = a->bias;

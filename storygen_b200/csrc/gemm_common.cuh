@@ -1,0 +1,275 @@
+// Shared pieces of the tcgen05 GEMM kernels (1-CTA gemm.cu, CTA-pair gemm2.cu): parameters and the epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace sg {
+
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // one 128-byte swizzle atom of bf16
+constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 2 epilogue warpgroups
+constexpr int kEpiWarps = 8;
+
+
+struct GemmKParams {
+  CUtensorMap a_maps[SG_MAX_SRC];
+  CUtensorMap b_map;
+  sg_seg segs[SG_MAX_SEGS];
+  int num_segs;
+  int total_kb;
+  int out_w, out_h, out_n;
+  int bw, bh, bn;
+  int tiles_x, tiles_y, tiles_n;  // M tiles = tiles_x * tiles_y * tiles_n
+  int num_n_tiles;
+  int N;
+  int mode;
+  int transpose_epi;  // 1: coalesce global traffic through a smem transpose (small-K GEMMs); 0: direct row stores
+  int out_channels;  // SG_EPI_NCHW_F32: number of valid output channels (<= 32)
+  float res_scale;
+  const float* bias;
+  const float* lane_bias;
+  long long ld_lane_bias;
+  const bf16* residual;
+  long long ldr;
+  bf16* out;
+  long long ldo;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int kScratchBytes = kEpiWarps * 4096;  // per epilogue warp: 2 x [32 rows x 64 B] transpose buffers
+  static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// erf-GELU with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 output rounding):
+// 2 MUFU + ~10 FMA instead of the ~35-instruction erff(), which made the GEGLU epilogue the bottleneck.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * fast_exp2(-1.4426950408889634f * z * z);
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
+}
+
+
+// One output tile of the epilogue, executed by one epilogue warp (quarter = TMEM lane quarter it may access,
+// grp = epilogue warpgroup 0/1 taking the 32-column chunks c = grp, grp+2, ...).  t_row = TMEM address of this
+// warp's lanes at the accumulator's first column; tfull / tfull_phase = "accumulator complete" barrier.
+template <int BN, int MODE>
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt, const int nt, const uint32_t t_row,
+                                              uint8_t* scratch, const int quarter, const int grp, const int lane,
+                                              uint64_t* tfull, const uint32_t tfull_phase) {
+    // Phase A (row-per-thread, as delivered by tcgen05.ld 32x32b): + bias + time embedding, [GEGLU], -> bf16.
+  // Phase B (after a swizzled transpose through this warp's smem scratch): every global access of the
+  // warp covers 8 rows x 64 B (GEGLU: 16 rows x 32 B) instead of 32 rows x 16 B; the residual is added and
+  // the result stored there.  (acc + bias) is rounded to bf16 before the residual add, exactly like the
+  // reference's separate Linear / add ops under autocast.
+  const int r = quarter * 32 + lane;
+  constexpr int kChunks = BN / 32;
+  constexpr int kMine = (kChunks + 1) / 2;                     // chunks per warpgroup (<= 4)
+  constexpr int kLpr = (MODE == SG_EPI_GEGLU) ? 2 : 4;         // lanes per row in phase B
+  constexpr int kIter = (MODE == SG_EPI_GEGLU) ? 2 : 4;        // phase-B iterations per chunk
+  constexpr int kRpi = 32 / kLpr;                              // rows per phase-B iteration
+  constexpr int kRowBytes = (MODE == SG_EPI_GEGLU) ? 32 : 64;  // bf16 bytes per row per chunk
+  auto row_coords = [&](int mt, int rr, int& x, int& y, int& n) {
+    const int tx = mt % p.tiles_x;
+    const int ty = (mt / p.tiles_x) % p.tiles_y;
+    const int tn = mt / (p.tiles_x * p.tiles_y);
+    x = tx * p.bw + rr % p.bw;
+    y = ty * p.bh + (rr / p.bw) % p.bh;
+    n = tn * p.bn + rr / (p.bw * p.bh);
+  };
+  // scratch address of 16-byte piece `pc` of row `row` (XOR swizzle keeps both phases bank-conflict free)
+  auto sc_addr = [&](int buf, int row, int pc) -> uint4* {
+    const int sw = (MODE == SG_EPI_GEGLU) ? ((row >> 2) & 1) : ((row >> 1) & 3);
+    return reinterpret_cast<uint4*>(scratch + buf * 2048 + row * kRowBytes + ((pc ^ sw) << 4));
+  };
+      int x, y, n;
+  row_coords(mt, r, x, y, n);
+  const bool row_ok = (x < p.out_w) && (y < p.out_h) && (n < p.out_n);
+  const float* lane_bias_row =
+      (p.lane_bias != nullptr) ? p.lane_bias + static_cast<long long>(n) * p.ld_lane_bias : nullptr;
+  // phase-B rows of this lane
+  long long mB[kIter];
+  bool okB[kIter];
+  if constexpr (MODE != SG_EPI_NCHW_F32) {
+#pragma unroll
+    for (int i = 0; i < kIter; ++i) {
+      int xb, yb, nb;
+      row_coords(mt, quarter * 32 + i * kRpi + lane / kLpr, xb, yb, nb);
+      okB[i] = (xb < p.out_w) && (yb < p.out_h) && (nb < p.out_n);
+      mB[i] = (static_cast<long long>(nb) * p.out_h + yb) * p.out_w + xb;
+    }
+  }
+  // Residual prefetch (coalesced, phase-B mapping) BEFORE the accumulator is awaited: its DRAM latency
+  // overlaps the tile's main loop.
+  uint4 res[kMine][4];
+  const bool use_res = (MODE == SG_EPI_LINEAR) && (p.residual != nullptr);
+  const bool tr = (p.transpose_epi != 0);  // kernel-uniform
+  if constexpr (MODE == SG_EPI_LINEAR) {
+    if (use_res) {
+#pragma unroll
+      for (int ci = 0; ci < kMine; ++ci) {
+        const int c = grp + 2 * ci;
+        const int col0 = nt * BN + c * 32;
+        if (c < kChunks && col0 < p.N) {
+          if (tr) {  // phase-B mapping: 8 rows x 64 B per warp instruction
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (okB[i])
+                res[ci][i] = __ldg(reinterpret_cast<const uint4*>(p.residual + mB[i] * p.ldr + col0 + (lane & 3) * 8));
+          } else if (row_ok) {  // own row, 4 x 16 B
+            const long long m = (static_cast<long long>(n) * p.out_h + y) * p.out_w + x;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              res[ci][i] = __ldg(reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col0) + i);
+          }
+        }
+      }
+    }
+  }
+
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  // TMEM loads are double-buffered where registers allow (the LINEAR mode holds the residual prefetch;
+  // there the second warp of the sub-partition hides the TMEM latency instead)
+  constexpr bool kDouble = (MODE != SG_EPI_LINEAR);
+  uint32_t v[kDouble ? 2 : 1][32];
+  if (kDouble && grp < kChunks) tmem_ld32(t_row + grp * 32, v[0]);
+#pragma unroll
+  for (int ci = 0; ci < kMine; ++ci) {
+    const int c = grp + 2 * ci;
+    if (c < kChunks) {  // warp-uniform
+      if constexpr (!kDouble) tmem_ld32(t_row + c * 32, v[0]);
+      tmem_ld_wait();
+      if (kDouble && ci + 1 < kMine && c + 2 < kChunks)
+        tmem_ld32(t_row + (c + 2) * 32, v[(ci + 1) & 1]);  // overlaps the math below
+      const int col0 = nt * BN + c * 32;
+      if (col0 < p.N) {  // warp-uniform
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[kDouble ? (ci & 1) : 0][j]);
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 bb = __ldg(b4 + j);
+            f[4 * j + 0] += bb.x;
+            f[4 * j + 1] += bb.y;
+            f[4 * j + 2] += bb.z;
+            f[4 * j + 3] += bb.w;
+          }
+        }
+        if (lane_bias_row != nullptr && row_ok) {
+          const float4* b4 = reinterpret_cast<const float4*>(lane_bias_row + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 bb = __ldg(b4 + j);
+            f[4 * j + 0] += bb.x;
+            f[4 * j + 1] += bb.y;
+            f[4 * j + 2] += bb.z;
+            f[4 * j + 3] += bb.w;
+          }
+        }
+        if constexpr (MODE == SG_EPI_NCHW_F32) {
+          // final conv: fp32 NCHW store of the first out_channels columns (coalesced along x)
+          if (c == 0 && row_ok) {
+            float* of = reinterpret_cast<float*>(p.out);
+            const long long plane = static_cast<long long>(p.out_h) * p.out_w;
+            const long long base =
+                static_cast<long long>(n) * p.out_channels * plane + static_cast<long long>(y) * p.out_w + x;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < p.out_channels) of[base + j * plane] = f[j];
+          }
+        } else if (MODE == SG_EPI_LINEAR && !tr) {
+          // direct path (large K: the epilogue is hidden behind the main loop and extra smem traffic would
+          // steal operand bandwidth from the tensor core): own row, 4 x 16-byte stores
+          if (row_ok) {
+            const long long m = (static_cast<long long>(n) * p.out_h + y) * p.out_w + x;
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + m * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q;
+              q.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              if (use_res) {
+                const uint4 rq = res[ci][j];
+                float2 a0 = unpack_bf16x2(q.x), a1 = unpack_bf16x2(q.y), a2 = unpack_bf16x2(q.z), a3 = unpack_bf16x2(q.w);
+                float2 r0 = unpack_bf16x2(rq.x), r1 = unpack_bf16x2(rq.y), r2 = unpack_bf16x2(rq.z), r3 = unpack_bf16x2(rq.w);
+                q.x = pack_bf16x2(fmaf(p.res_scale, r0.x, a0.x), fmaf(p.res_scale, r0.y, a0.y));
+                q.y = pack_bf16x2(fmaf(p.res_scale, r1.x, a1.x), fmaf(p.res_scale, r1.y, a1.y));
+                q.z = pack_bf16x2(fmaf(p.res_scale, r2.x, a2.x), fmaf(p.res_scale, r2.y, a2.y));
+                q.w = pack_bf16x2(fmaf(p.res_scale, r3.x, a3.x), fmaf(p.res_scale, r3.y, a3.y));
+              }
+              o4[j] = q;
+            }
+          }
+        } else {
+          const int buf = ci & 1;
+          // ---- phase A -> scratch
+          if constexpr (MODE == SG_EPI_LINEAR) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q;
+              q.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              *sc_addr(buf, lane, j) = q;
+            }
+          } else {
+            // GEGLU: columns [0,16) = value, [16,32) = gate (weights pre-interleaved on the host)
+            float g[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g[j] = f[j] * gelu_erf(f[16 + j]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              uint4 q;
+              q.x = pack_bf16x2(g[8 * j + 0], g[8 * j + 1]);
+              q.y = pack_bf16x2(g[8 * j + 2], g[8 * j + 3]);
+              q.z = pack_bf16x2(g[8 * j + 4], g[8 * j + 5]);
+              q.w = pack_bf16x2(g[8 * j + 6], g[8 * j + 7]);
+              *sc_addr(buf, lane, j) = q;
+            }
+          }
+          __syncwarp();
+          // ---- phase B: coalesced residual add + store
+          const int ocol = (MODE == SG_EPI_GEGLU) ? (col0 >> 1) : col0;
+#pragma unroll
+          for (int i = 0; i < kIter; ++i) {
+            uint4 q = *sc_addr(buf, i * kRpi + lane / kLpr, lane % kLpr);
+            if (okB[i]) {
+              if constexpr (MODE == SG_EPI_LINEAR) {
+                if (use_res) {
+                  const uint4 rq = res[ci][i];
+                  float2 a0 = unpack_bf16x2(q.x), a1 = unpack_bf16x2(q.y), a2 = unpack_bf16x2(q.z), a3 = unpack_bf16x2(q.w);
+                  float2 r0 = unpack_bf16x2(rq.x), r1 = unpack_bf16x2(rq.y), r2 = unpack_bf16x2(rq.z), r3 = unpack_bf16x2(rq.w);
+                  q.x = pack_bf16x2(fmaf(p.res_scale, r0.x, a0.x), fmaf(p.res_scale, r0.y, a0.y));
+                  q.y = pack_bf16x2(fmaf(p.res_scale, r1.x, a1.x), fmaf(p.res_scale, r1.y, a1.y));
+                  q.z = pack_bf16x2(fmaf(p.res_scale, r2.x, a2.x), fmaf(p.res_scale, r2.y, a2.y));
+                  q.w = pack_bf16x2(fmaf(p.res_scale, r3.x, a3.x), fmaf(p.res_scale, r3.y, a3.y));
+                }
+              }
+              *reinterpret_cast<uint4*>(p.out + mB[i] * p.ldo + ocol + (lane % kLpr) * 8) = q;
+            }
+          }
+          // the next use of this scratch buffer is two chunks later, after another __syncwarp
+        }
+      }
+    }
+  }
+}
+
+}  // namespace sg

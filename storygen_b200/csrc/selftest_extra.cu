@@ -103,7 +103,13 @@ static void run_attn_case(const char* name, int D, int H, int n_lanes, int n_kv_
   if (kv_map_d) cudaFree(kv_map_d);
 }
 
+void test_ubench();
+void test_ubench_mma();
+void test_timeline();
 void test_extra() {
+  test_ubench();
+  test_ubench_mma();
+  test_timeline();
   run_attn_case("attn d40 self 2x8 nq=nk=256", 40, 8, 2, 2, 256, 256, 1.f, false, {});
   run_attn_case("attn d40 1 tile nq=128 nk=128 h=1", 40, 1, 1, 1, 128, 128, 1.f, false, {});
   run_attn_case("attn d40 text nq=256 nk=77 (masked tail)", 40, 8, 2, 2, 256, 77, 1.f, false, {});
@@ -117,4 +123,175 @@ void test_extra() {
   run_attn_case("attn long d160 nq=256 nk=1536", 160, 4, 1, 1, 256, 1536, 3.f, false, {});
   run_attn_case("attn long d80 nq=256 nk=3072", 80, 2, 1, 1, 256, 3072, 3.f, false, {});
   run_attn_case("attn long d40 nq=512 nk=4096", 40, 2, 1, 1, 512, 4096, 4.f, false, {});
+}
+
+// ---------------------------------------------------------------------------------------------
+// micro-benchmarks (./selftest "ubench"): TMEM read throughput, MUFU.EX2 throughput
+// ---------------------------------------------------------------------------------------------
+#include "ptx.cuh"
+__global__ void ubench_tmem_ld(int iters, long long* cycles, float* sink) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) sg::tmem_alloc(&slot, 512);
+  sg::tc_fence_before();
+  __syncthreads();
+  sg::tc_fence_after();
+  const uint32_t base = slot + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  float acc = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t v[4][32];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sg::tmem_ld32(base + ((it & 1) * 256) + c * 32, v[c]);
+    sg::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc += __uint_as_float(v[c][0]) + __uint_as_float(v[c][17]) + __uint_as_float(v[c][31]);
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  __syncthreads();
+  if (warp == 0) sg::tmem_dealloc(slot, 512);
+}
+__global__ void ubench_mufu(int iters, long long* cycles, float* sink) {
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = -0.001f * (threadIdx.x + i);
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = sg::fast_exp2(x[i]) - 1.0009f;
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  float a = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a += x[i];
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = a;
+}
+void test_timeline() {
+  if (!want("timeline")) return;
+  const int D = 40, H = 8, C = H * D, nq = 4096, nk = 4096, lanes = 3;
+  HostBf Q, K, V, O;
+  Q.init(1ll * lanes * nq * C, 1.f);
+  K.init(1ll * lanes * nk * C, 1.f);
+  V.init(1ll * lanes * nk * C, 1.f);
+  O.zeros(1ll * lanes * nq * C);
+  long long* dbg;
+  CK(cudaMalloc(&dbg, 12 * 16 * 8 * 8));
+  CK(cudaMemset(dbg, 0, 12 * 16 * 8 * 8));
+  sg_attn_args a;
+  memset(&a, 0, sizeof(a));
+  a.q = Q.d; a.k = K.d; a.v = V.d; a.o = O.d;
+  a.q_stride_n = 1ll * nq * C; a.q_stride_t = C; a.k_stride_n = 1ll * nk * C; a.k_stride_t = C;
+  a.v_stride_n = 1ll * nk * C; a.v_stride_t = C; a.o_stride_n = 1ll * nq * C; a.o_stride_t = C;
+  a.n_lanes = lanes; a.n_heads = H; a.head_dim = D; a.nq = nq; a.nk = nk; a.scale = 1.f / sqrtf(40.f);
+  a.debug_timeline = reinterpret_cast<int64_t*>(dbg);
+  for (int rep = 0; rep < 2; ++rep) { int rc = sg_attention(&a, nullptr); CK(cudaDeviceSynchronize()); if (rc) printf("rc=%d\n", rc); }
+  std::vector<long long> h(12 * 16 * 8);
+  CK(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+  long long t0 = h[(4 * 16 + 2) * 8 + 0];
+  printf("[timeline] clocks relative to warp4 tile2 start; slots: 0=before s_full wait 1=S ready 2=S in regs 3=max done 4=exp unit granted 5=exps+Pstore issued 6=P published\n");
+  for (int w : {4, 8}) for (int j = 2; j < 8; ++j) {
+    printf("[timeline] warp %2d tile %d:", w, j);
+    for (int k = 0; k < 7; ++k) printf(" %7lld", h[(w * 16 + j) * 8 + k] - t0);
+    printf("\n");
+  }
+  for (int j = 2; j < 8; ++j)
+    printf("[timeline] mma issue tile %d: QK_0 %7lld  PV_0 %7lld  QK_1 %7lld  PV_1 %7lld\n", j, h[(16 + j) * 8 + 0] - t0,
+           h[(16 + j) * 8 + 1] - t0, h[(16 + j) * 8 + 2] - t0, h[(16 + j) * 8 + 3] - t0);
+  cudaFree(dbg);
+}
+void test_ubench() {
+  if (!want("ubench")) return;
+  long long* cyc;
+  float* sink;
+  CK(cudaMalloc(&cyc, 8 * 1024));
+  CK(cudaMalloc(&sink, 4 * 1024 * 1024));
+  for (int warps : {4, 8, 16}) {
+    const int iters = 2000;
+    ubench_tmem_ld<<<148, warps * 32>>>(iters, cyc, sink);
+    CK(cudaDeviceSynchronize());
+    long long h;
+    CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    const double bytes = static_cast<double>(iters) * warps * 4 * 32 * 32 * 4;  // per SM
+    printf("[ubench] tmem_ld 32x32b.x32: %2d warps/SM: %.1f cycles per 128-col row-block per warp, %.1f B/clk/SM\n", warps,
+           static_cast<double>(h) / iters, bytes / h);
+  }
+  for (int warps : {4, 8, 16}) {
+    const int iters = 4000;
+    ubench_mufu<<<148, warps * 32>>>(iters, cyc, sink);
+    CK(cudaDeviceSynchronize());
+    long long h;
+    CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("[ubench] ex2.approx.ftz.f32 (+1 FADD): %2d warps/SM: %.2f lane-results/clk/SM\n", warps,
+           static_cast<double>(iters) * 16 * warps * 32 / h);
+  }
+  cudaFree(cyc);
+  cudaFree(sink);
+}
+
+// tcgen05.mma issue/latency: `chains` independent accumulators used round-robin (1 = fully dependent stream)
+template <int N>
+__global__ void ubench_mma(int iters, int chains, int use_ts, long long* cycles) {
+  extern __shared__ uint8_t smem_raw_u[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_u) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { sg::mbar_init(&bar, 1); sg::fence_barrier_init(); }
+  sg::fence_proxy_async_smem();
+  if (threadIdx.x < 32) sg::tmem_alloc(&slot, 512);
+  sg::tc_fence_before();
+  __syncthreads();
+  sg::tc_fence_after();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = sg::make_idesc_bf16(128, N, 0, 0);
+    const uint64_t a_desc = sg::make_smem_desc(sg::smem_u32(smem), 16, 1024, sg::kLayoutSW128);
+    const uint64_t b_desc = sg::make_smem_desc(sg::smem_u32(smem + 16384), 16, 1024, sg::kLayoutSW128);
+    // accumulators at columns 0, N (2 chains) or 0, 128, 256, 384 (4 chains, N <= 128); chains is a power of two
+    const uint32_t stride = (chains == 4) ? 128u : static_cast<uint32_t>(N);
+    const uint32_t mask = static_cast<uint32_t>(chains - 1);
+    const long long t0 = clock64();
+#pragma unroll 8
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = slot + (static_cast<uint32_t>(it) & mask) * stride;
+      const uint64_t koff = 2 * (it & 3);
+      if (use_ts) sg::umma_ts(d, slot + 448, b_desc + koff, idesc, 1);
+      else sg::umma_ss(d, a_desc + koff, b_desc + koff, idesc, 1);
+    }
+    sg::umma_commit(&bar);
+    sg::mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) sg::tmem_dealloc(slot, 512);
+}
+template <int N>
+static void run_mma_bench(long long* cyc) {
+  CK(cudaFuncSetAttribute(ubench_mma<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024));
+  for (int ts = 0; ts < 2; ++ts)
+    for (int chains : {1, 2, 4}) {
+      if ((chains == 2 && 2 * N > 448) || (chains == 4 && N > 112)) continue;  // keep clear of the TS operand at col 448
+      const int iters = 512;
+      ubench_mma<N><<<148, 128, 60 * 1024>>>(iters, chains, ts, cyc);
+      CK(cudaDeviceSynchronize());
+      long long h;
+      CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+      printf("[ubench] tcgen05.mma M128 N%-3d K16 %s: %d accumulator chain(s): %.1f clk per MMA (math %.0f clk)\n", N,
+             ts ? "TS" : "SS", chains, static_cast<double>(h) / iters, 128.0 * N / 256.0);
+    }
+}
+void test_ubench_mma() {
+  if (!want("ubench")) return;
+  long long* cyc;
+  CK(cudaMalloc(&cyc, 8 * 1024));
+  run_mma_bench<64>(cyc);
+  run_mma_bench<128>(cyc);
+  run_mma_bench<160>(cyc);
+  run_mma_bench<256>(cyc);
+  cudaFree(cyc);
 }

@@ -13,6 +13,7 @@ from . import _lib
 from ._lib import SG_EPI_GEGLU, SG_EPI_LINEAR, SG_EPI_NCHW_F32, SgAttnArgs, SgGemmArgs
 
 BF16 = torch.bfloat16
+TRACE = None  # set to a list to record (kernel, shape...) of every launch, in order (profiling aid)
 
 
 def _stream() -> int:
@@ -61,7 +62,10 @@ class Src:
 
 
 def tile_box(w: int, h: int, n: int) -> Tuple[int, int, int]:
-    """128-row tile as a bw x bh x bn box of the output pixel grid."""
+    """128-row tile as a bw x bh x bn box of the output pixel grid.  A plain (M, K) matrix (h == n == 1)
+    always uses 128 consecutive rows: TMA clips the ragged last tile, the epilogue masks it."""
+    if h == 1 and n == 1:
+        return 128, 1, 1
     bw = math.gcd(w, 128)
     bh = math.gcd(h, 128 // bw)
     return bw, bh, 128 // (bw * bh)
@@ -99,6 +103,8 @@ def gemm(srcs: Sequence[Src], segs: Sequence[Tuple[int, int, int, int, int]], gr
     a.ldr = residual.shape[-1] if residual is not None else 0
     a.out = out.data_ptr()
     a.ldo = out.shape[-1]
+    if TRACE is not None:
+        TRACE.append(("gemm", grid[0] * grid[1] * grid[2], int(a.N), int(a.Ktot), len(segs), mode))
     _lib.check(_lib.load().sg_gemm(C.byref(a), _stream()), "sg_gemm")
     return out
 
@@ -131,6 +137,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     a.n_kv_lanes = n_kv_lanes
     a.kv_map = _ptr(kv_map)
     a.scale = head_dim ** -0.5
+    if TRACE is not None:
+        TRACE.append(("attn", n_lanes, n_heads, head_dim, nq, nk))
     _lib.check(_lib.load().sg_attention(C.byref(a), _stream()), "sg_attention")
     return out
 
