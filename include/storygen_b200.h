@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 6
+#define SG_ABI_VERSION 7
 
 #define SG_ERR_SHAPE (-1)   /* unsupported / inconsistent shape            */
 #define SG_ERR_ALIGN (-2)   /* pointer or stride not 16-byte aligned        */
@@ -98,6 +98,7 @@ typedef struct sg_gemm_args {
   int64_t ldr;
   void* out; /* bf16 [M, ldo] */
   int64_t ldo;
+  int64_t* debug_timeline; /* bring-up aid: device int64[10*8*8] phase clocks of CTA 0, or NULL */
 } sg_gemm_args;
 
 int sg_gemm(const sg_gemm_args* args, void* stream);

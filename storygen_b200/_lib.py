@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstorygen_b200.so")
 
-SG_ABI_VERSION = 6
+SG_ABI_VERSION = 7
 SG_MAX_SRC = 4
 SG_MAX_SEGS = 24
 SG_EPI_LINEAR = 0
@@ -41,7 +41,7 @@ class SgGemmArgs(C.Structure):
                 ("bw", C.c_int32), ("bh", C.c_int32), ("bn", C.c_int32), ("b", C.c_void_p), ("N", C.c_int64),
                 ("Ktot", C.c_int64), ("mode", C.c_int32), ("out_channels", C.c_int32), ("res_scale", C.c_float), ("bias", C.c_void_p),
                 ("lane_bias", C.c_void_p), ("ld_lane_bias", C.c_int64), ("residual", C.c_void_p),
-                ("ldr", C.c_int64), ("out", C.c_void_p), ("ldo", C.c_int64)]
+                ("ldr", C.c_int64), ("out", C.c_void_p), ("ldo", C.c_int64), ("debug_timeline", C.c_void_p)]
 
 
 class SgAttnArgs(C.Structure):

@@ -98,9 +98,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int mma_tile = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (p.dbg != nullptr && blockIdx.x == 0 && mma_tile < 8) p.dbg[(1 * 8 + mma_tile) * 8 + 0] = clock64();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < p.total_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -121,6 +123,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           }
         }
         umma_commit(&tfull_bar[acc]);
+        if (p.dbg != nullptr && blockIdx.x == 0 && mma_tile < 8) p.dbg[(1 * 8 + mma_tile) * 8 + 1] = clock64();
+        ++mma_tile;
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -131,14 +135,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // ===================== epilogue (see gemm_common.cuh::epilogue_tile) =====================
     const int quarter = warp & 3;     // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;  // epilogue warpgroup 0 / 1
-    uint8_t* scratch = epi_scratch + (warp - 2) * 4096;
+    uint8_t* scratch = epi_scratch + (warp - 2) * Cfg::kWarpScratch;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int tile_ord = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.num_n_tiles;
       const int nt = tile - mt * p.num_n_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_tile<BN, MODE>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase);
+      epilogue_tile<BN, MODE>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase, tile_ord, warp);
+      ++tile_ord;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -192,7 +198,7 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   if (a == nullptr || a->b == nullptr || a->out == nullptr) return SG_ERR_ARG;
   if (a->num_src < 1 || a->num_src > SG_MAX_SRC || a->num_segs < 1 || a->num_segs > SG_MAX_SEGS)
     return SG_ERR_ARG;
-  if (a->bw * a->bh * a->bn != kBM || a->bw > 256 || a->bh > 256 || a->bn > 256) return SG_ERR_SHAPE;
+  if (a->bw * a->bh * a->bn != kBM || a->bw < 1 || a->bh < 1 || a->bn < 1) return SG_ERR_SHAPE;  // => all powers of two
   if (a->N % 32 != 0 || a->Ktot % kBK != 0) return SG_ERR_SHAPE;
   if (a->mode != SG_EPI_LINEAR && a->mode != SG_EPI_GEGLU && a->mode != SG_EPI_NCHW_F32) return SG_ERR_ARG;
   if (a->mode == SG_EPI_NCHW_F32 && (a->out_channels < 1 || a->out_channels > 32 || a->N != 32)) return SG_ERR_SHAPE;
@@ -241,6 +247,8 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   kp.bw = a->bw;
   kp.bh = a->bh;
   kp.bn = a->bn;
+  kp.bw_log2 = 31 - __builtin_clz(static_cast<unsigned>(a->bw));
+  kp.bh_log2 = 31 - __builtin_clz(static_cast<unsigned>(a->bh));
   kp.tiles_x = (a->out_w + a->bw - 1) / a->bw;
   kp.tiles_y = (a->out_h + a->bh - 1) / a->bh;
   kp.tiles_n = (a->out_n + a->bn - 1) / a->bn;
@@ -257,6 +265,7 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   kp.ldr = a->ldr;
   kp.out = static_cast<bf16*>(a->out);
   kp.ldo = a->ldo;
+  kp.dbg = reinterpret_cast<long long*>(a->debug_timeline);
 
   const int num_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n * kp.num_n_tiles;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);

@@ -19,6 +19,7 @@ struct GemmKParams {
   int total_kb;
   int out_w, out_h, out_n;
   int bw, bh, bn;
+  int bw_log2, bh_log2;  // bw, bh are powers of two (bw * bh * bn == 128)
   int tiles_x, tiles_y, tiles_n;  // M tiles = tiles_x * tiles_y * tiles_n
   int num_n_tiles;
   int N;
@@ -33,6 +34,7 @@ struct GemmKParams {
   long long ldr;
   bf16* out;
   long long ldo;
+  long long* dbg;  // bring-up aid: phase clocks of CTA 0 (NULL in production)
 };
 
 template <int BN>
@@ -42,8 +44,10 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kScratchBytes = kEpiWarps * 4096;  // per epilogue warp: 2 x [32 rows x 64 B] transpose buffers
-  static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kWarpScratch = 2048 + 128;  // per epilogue warp: [32 rows x 64 B] transpose buffer + 32 bias floats
+  static constexpr int kScratchBytes = kEpiWarps * kWarpScratch;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align*/ + 128 /*barriers*/;
+  static_assert(kSmemBytes <= 231424, "exceeds the 227 KB - 1 KB (reserved) dynamic shared memory limit");
 };
 
 // erf-GELU with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 output rounding):
@@ -67,7 +71,10 @@ __device__ __forceinline__ float gelu_erf(float x) {
 template <int BN, int MODE>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt, const int nt, const uint32_t t_row,
                                               uint8_t* scratch, const int quarter, const int grp, const int lane,
-                                              uint64_t* tfull, const uint32_t tfull_phase) {
+                                              uint64_t* tfull, const uint32_t tfull_phase, const int tile_ord = 0, const int warp_id = 0) {
+  const bool dbg_on = (p.dbg != nullptr) && blockIdx.x == 0 && lane == 0 && tile_ord < 8;
+#define SG_GT(slot) do { if (dbg_on) p.dbg[(warp_id * 8 + tile_ord) * 8 + (slot)] = clock64(); } while (0)
+  SG_GT(0);
     // Phase A (row-per-thread, as delivered by tcgen05.ld 32x32b): + bias + time embedding, [GEGLU], -> bf16.
   // Phase B (after a swizzled transpose through this warp's smem scratch): every global access of the
   // warp covers 8 rows x 64 B (GEGLU: 16 rows x 32 B) instead of 32 rows x 16 B; the residual is added and
@@ -80,21 +87,25 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
   constexpr int kIter = (MODE == SG_EPI_GEGLU) ? 2 : 4;        // phase-B iterations per chunk
   constexpr int kRpi = 32 / kLpr;                              // rows per phase-B iteration
   constexpr int kRowBytes = (MODE == SG_EPI_GEGLU) ? 32 : 64;  // bf16 bytes per row per chunk
-  auto row_coords = [&](int mt, int rr, int& x, int& y, int& n) {
-    const int tx = mt % p.tiles_x;
-    const int ty = (mt / p.tiles_x) % p.tiles_y;
-    const int tn = mt / (p.tiles_x * p.tiles_y);
-    x = tx * p.bw + rr % p.bw;
-    y = ty * p.bh + (rr / p.bw) % p.bh;
-    n = tn * p.bn + rr / (p.bw * p.bh);
+  const int tx = mt % p.tiles_x;
+  const int ty = (mt / p.tiles_x) % p.tiles_y;
+  const int tn = mt / (p.tiles_x * p.tiles_y);
+  auto row_coords = [&](int rr, int& x, int& y, int& n) {
+    x = tx * p.bw + (rr & (p.bw - 1));
+    y = ty * p.bh + ((rr >> p.bw_log2) & (p.bh - 1));
+    n = tn * p.bn + (rr >> (p.bw_log2 + p.bh_log2));
   };
-  // scratch address of 16-byte piece `pc` of row `row` (XOR swizzle keeps both phases bank-conflict free)
-  auto sc_addr = [&](int buf, int row, int pc) -> uint4* {
+  // shared-window address of 16-byte piece `pc` of row `row` (XOR swizzle keeps both phases conflict free)
+  const uint32_t scratch_u32 = smem_u32(scratch);
+  auto sc_addr = [&](int buf, int row, int pc) -> uint32_t {
     const int sw = (MODE == SG_EPI_GEGLU) ? ((row >> 2) & 1) : ((row >> 1) & 3);
-    return reinterpret_cast<uint4*>(scratch + buf * 2048 + row * kRowBytes + ((pc ^ sw) << 4));
+    return scratch_u32 + buf * 2048 + row * kRowBytes + ((pc ^ sw) << 4);
   };
-      int x, y, n;
-  row_coords(mt, r, x, y, n);
+  // bias (+ per-image time-embedding bias) of a chunk: one coalesced 128-byte load per warp, prefetched one
+  // chunk ahead into a register, staged in this warp's scratch and read back as broadcasts
+  const uint32_t bias_u32 = scratch_u32 + 2048;
+  int x, y, n;
+  row_coords(r, x, y, n);
   const bool row_ok = (x < p.out_w) && (y < p.out_h) && (n < p.out_n);
   const float* lane_bias_row =
       (p.lane_bias != nullptr) ? p.lane_bias + static_cast<long long>(n) * p.ld_lane_bias : nullptr;
@@ -105,7 +116,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
 #pragma unroll
     for (int i = 0; i < kIter; ++i) {
       int xb, yb, nb;
-      row_coords(mt, quarter * 32 + i * kRpi + lane / kLpr, xb, yb, nb);
+      row_coords(quarter * 32 + i * kRpi + lane / kLpr, xb, yb, nb);
       okB[i] = (xb < p.out_w) && (yb < p.out_h) && (nb < p.out_n);
       mB[i] = (static_cast<long long>(nb) * p.out_h + yb) * p.out_w + xb;
     }
@@ -138,8 +149,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
     }
   }
 
+  float bias_pre = 0.f;
+  if (p.bias != nullptr && grp < kChunks && nt * BN + grp * 32 < p.N) bias_pre = __ldg(p.bias + nt * BN + grp * 32 + lane);
+  SG_GT(1);
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
+  SG_GT(2);
   // TMEM loads are double-buffered where registers allow (the LINEAR mode holds the residual prefetch;
   // there the second warp of the sub-partition hides the TMEM latency instead)
   constexpr bool kDouble = (MODE != SG_EPI_LINEAR);
@@ -159,14 +174,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[kDouble ? (ci & 1) : 0][j]);
         if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+          sts32(bias_u32 + lane * 4, __float_as_uint(bias_pre));
+          if (ci + 1 < kMine && c + 2 < kChunks && col0 + 64 < p.N) bias_pre = __ldg(p.bias + col0 + 64 + lane);
+          __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 bb = __ldg(b4 + j);
-            f[4 * j + 0] += bb.x;
-            f[4 * j + 1] += bb.y;
-            f[4 * j + 2] += bb.z;
-            f[4 * j + 3] += bb.w;
+            const uint4 bb = lds128(bias_u32 + j * 16);  // same address in every lane: broadcast
+            f[4 * j + 0] += __uint_as_float(bb.x);
+            f[4 * j + 1] += __uint_as_float(bb.y);
+            f[4 * j + 2] += __uint_as_float(bb.z);
+            f[4 * j + 3] += __uint_as_float(bb.w);
           }
         }
         if (lane_bias_row != nullptr && row_ok) {
@@ -217,7 +234,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
             }
           }
         } else {
-          const int buf = ci & 1;
+          const int buf = 0;
           // ---- phase A -> scratch
           if constexpr (MODE == SG_EPI_LINEAR) {
 #pragma unroll
@@ -227,7 +244,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
               q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
               q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
               q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              *sc_addr(buf, lane, j) = q;
+              sts128(sc_addr(buf, lane, j), q);
             }
           } else {
             // GEGLU: columns [0,16) = value, [16,32) = gate (weights pre-interleaved on the host)
@@ -241,7 +258,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
               q.y = pack_bf16x2(g[8 * j + 2], g[8 * j + 3]);
               q.z = pack_bf16x2(g[8 * j + 4], g[8 * j + 5]);
               q.w = pack_bf16x2(g[8 * j + 6], g[8 * j + 7]);
-              *sc_addr(buf, lane, j) = q;
+              sts128(sc_addr(buf, lane, j), q);
             }
           }
           __syncwarp();
@@ -249,7 +266,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
           const int ocol = (MODE == SG_EPI_GEGLU) ? (col0 >> 1) : col0;
 #pragma unroll
           for (int i = 0; i < kIter; ++i) {
-            uint4 q = *sc_addr(buf, i * kRpi + lane / kLpr, lane % kLpr);
+            uint4 q = lds128(sc_addr(buf, i * kRpi + lane / kLpr, lane % kLpr));
             if (okB[i]) {
               if constexpr (MODE == SG_EPI_LINEAR) {
                 if (use_res) {
@@ -265,11 +282,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
               *reinterpret_cast<uint4*>(p.out + mB[i] * p.ldo + ocol + (lane % kLpr) * 8) = q;
             }
           }
-          // the next use of this scratch buffer is two chunks later, after another __syncwarp
+          __syncwarp();  // phase-B reads done before the next chunk's phase-A writes
         }
       }
     }
   }
+  SG_GT(3);
+#undef SG_GT
 }
 
 }  // namespace sg

@@ -250,6 +250,22 @@ __device__ __forceinline__ void tmem_st_wait() {
 }
 
 // ----------------------------------------------------------------------------------------------
+// explicit shared-memory accesses (a generic pointer derived from dynamic smem makes the compiler emit
+// generic LD/ST with long-scoreboard latency; these always emit LDS/STS)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

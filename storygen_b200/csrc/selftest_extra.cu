@@ -105,11 +105,15 @@ static void run_attn_case(const char* name, int D, int H, int n_lanes, int n_kv_
 
 void test_ubench();
 void test_ubench_mma();
+void test_ubench_cp();
 void test_timeline();
+void test_gemm_timeline();
 void test_extra() {
   test_ubench();
   test_ubench_mma();
+  test_ubench_cp();
   test_timeline();
+  test_gemm_timeline();
   run_attn_case("attn d40 self 2x8 nq=nk=256", 40, 8, 2, 2, 256, 256, 1.f, false, {});
   run_attn_case("attn d40 1 tile nq=128 nk=128 h=1", 40, 1, 1, 1, 128, 128, 1.f, false, {});
   run_attn_case("attn d40 text nq=256 nk=77 (masked tail)", 40, 8, 2, 2, 256, 77, 1.f, false, {});
@@ -204,6 +208,35 @@ void test_timeline() {
            h[(16 + j) * 8 + 1] - t0, h[(16 + j) * 8 + 2] - t0, h[(16 + j) * 8 + 3] - t0);
   cudaFree(dbg);
 }
+void test_gemm_timeline() {
+  if (!want("gtimeline")) return;
+  const int M = 98304, N = 2560, K = 320;
+  HostBf A, B, O;
+  A.init(1ll * M * K, 1.f);
+  B.init(1ll * N * K, 0.05f);
+  O.zeros(1ll * M * N);
+  long long* dbg;
+  CK(cudaMalloc(&dbg, 10 * 8 * 8 * 8));
+  CK(cudaMemset(dbg, 0, 10 * 8 * 8 * 8));
+  sg_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.num_src = 1; a.src[0].ptr = A.d; a.src[0].dim_c = K; a.src[0].dim_w = M; a.src[0].dim_h = 1; a.src[0].dim_n = 1;
+  a.src[0].stride_w = K; a.src[0].stride_h = 1ll * M * K; a.src[0].stride_n = 1ll * M * K;
+  a.num_segs = 1; a.segs[0].src = 0; a.segs[0].nkb = K / 64;
+  a.out_w = M; a.out_h = 1; a.out_n = 1; a.bw = 128; a.bh = 1; a.bn = 1;
+  a.b = B.d; a.N = N; a.Ktot = K; a.mode = SG_EPI_LINEAR; a.out = O.d; a.ldo = N; a.debug_timeline = reinterpret_cast<int64_t*>(dbg);
+  for (int rep = 0; rep < 2; ++rep) { int rc = sg_gemm(&a, nullptr); CK(cudaDeviceSynchronize()); if (rc) printf("rc=%d\n", rc); }
+  std::vector<long long> h(10 * 8 * 8);
+  CK(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
+  const long long t0 = h[(1 * 8 + 1) * 8 + 0];
+  printf("[gtimeline] M=%d N=%d K=%d LINEAR; clocks relative to MMA start of tile 1\n", M, N, K);
+  for (int j = 1; j < 6; ++j)
+    printf("[gtimeline] tile %d: mma start %7lld issued %7lld | epi warp2: enter %7lld res-prefetch-done %7lld acc-ready %7lld done %7lld | epi warp6: enter %7lld acc-ready %7lld done %7lld\n", j,
+           h[(8 + j) * 8 + 0] - t0, h[(8 + j) * 8 + 1] - t0, h[(2 * 8 + j) * 8 + 0] - t0, h[(2 * 8 + j) * 8 + 1] - t0,
+           h[(2 * 8 + j) * 8 + 2] - t0, h[(2 * 8 + j) * 8 + 3] - t0, h[(6 * 8 + j) * 8 + 0] - t0, h[(6 * 8 + j) * 8 + 2] - t0,
+           h[(6 * 8 + j) * 8 + 3] - t0);
+  cudaFree(dbg);
+}
 void test_ubench() {
   if (!want("ubench")) return;
   long long* cyc;
@@ -293,5 +326,67 @@ void test_ubench_mma() {
   run_mma_bench<128>(cyc);
   run_mma_bench<160>(cyc);
   run_mma_bench<256>(cyc);
+  cudaFree(cyc);
+}
+
+// TS-mode GEMM feasibility: per k-block 4 x tcgen05.cp (smem A [128 x 16] -> TMEM, 128x256b) + 4 x TS MMA
+template <int N>
+__global__ void ubench_cp_ts(int iters, int with_cp, int with_mma, long long* cycles) {
+  extern __shared__ uint8_t smem_raw_u2[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_u2) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { sg::mbar_init(&bar, 1); sg::fence_barrier_init(); }
+  sg::fence_proxy_async_smem();
+  if (threadIdx.x < 32) sg::tmem_alloc(&slot, 512);
+  sg::tc_fence_before();
+  __syncthreads();
+  sg::tc_fence_after();
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = sg::make_idesc_bf16(128, N, 0, 0);
+    const uint64_t a_desc = sg::make_smem_desc(sg::smem_u32(smem), 16, 1024, sg::kLayoutSW128);
+    const uint64_t b_desc = sg::make_smem_desc(sg::smem_u32(smem + 16384), 16, 1024, sg::kLayoutSW128);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t a_tmem = slot + 256 + (it & 1) * 32;  // double-buffered A region: 8 columns per k16 step
+      if (with_cp) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(a_tmem + k * 8), "l"(a_desc + 2 * k) : "memory");
+      }
+      if (with_mma) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sg::umma_ts(slot, a_tmem + k * 8, b_desc + 2 * k, idesc, 1);
+      }
+    }
+    sg::umma_commit(&bar);
+    sg::mbar_wait(&bar, 0);
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) sg::tmem_dealloc(slot, 512);
+}
+void test_ubench_cp() {
+  if (!want("ubench")) return;
+  long long* cyc;
+  CK(cudaMalloc(&cyc, 8 * 1024));
+  CK(cudaFuncSetAttribute(ubench_cp_ts<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024));
+  CK(cudaFuncSetAttribute(ubench_cp_ts<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024));
+  const int iters = 256;
+  for (int mode = 0; mode < 3; ++mode) {
+    const int cp = (mode != 1), mma = (mode != 0);
+    long long h;
+    ubench_cp_ts<256><<<148, 128, 60 * 1024>>>(iters, cp, mma, cyc);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("[ubench] k-block (K=64) N=256: %s%s: %.1f clk per k-block (SS would be 774, math 512)\n", cp ? "4x tcgen05.cp " : "",
+           mma ? "4x TS mma" : "", static_cast<double>(h) / iters);
+    ubench_cp_ts<160><<<148, 128, 60 * 1024>>>(iters, cp, mma, cyc);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("[ubench] k-block (K=64) N=160: %s%s: %.1f clk per k-block (SS would be 668, math 320)\n", cp ? "4x tcgen05.cp " : "",
+           mma ? "4x TS mma" : "", static_cast<double>(h) / iters);
+  }
   cudaFree(cyc);
 }
