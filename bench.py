@@ -200,8 +200,15 @@ def kernel_rooflines(torch, peaks, lanes):
     b = torch.zeros(c, device=dev)
     t = timeit(lambda i: ops.gemm([Src.nhwc(xs[i])], taps3x3(0, c), (w, h, lanes), wt, ys[i], bias=b), 4)
     flops = 2.0 * lanes * h * w * c * 9 * c
+    # traffic = dram__bytes_read.sum + dram__bytes_write.sum of this kernel inside a step at 24 lanes (ncu --set full,
+    # profiles/r01_ncu_full_prof_conv_r01b.csv): 64.9 + 26.0 MB < 127.7 MB algorithmic (input still L2-resident)
+    traffic = 90911232 if lanes == 24 else None
     out["conv3x3_320_L0"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                             "frac": flops / t / 1e12 / peaks["tf_burst"], "traffic": None,
+                             "frac": flops / t / 1e12 / peaks["tf_burst"], "traffic": traffic,
+                             "algorithmic_bytes": 2 * lanes * h * w * c * 2 + 9 * c * c * 2,
+                             "note": "tcgen05.mma M128 N160 K16 (SS) costs 167 clk per instruction for 80 clk of math "
+                                     "(profiles/r01_ubench_mma_cost.log): a 1-CTA kernel of this tile shape tops out at ~48-52 % of "
+                                     "the tensor peak; cuBLAS' 1676 TFLOP/s 'measured peak' uses 256-wide 2-CTA tiles",
                              "flops_per_launch": flops, "ms_per_launch": t * 1e3, "lanes": lanes}
     # (2) L0 image cross-attention core: Nq = 4096, Nk = 3 * 4096, 8 heads x d40
     hd, heads, nq, nk = 40, 8, 4096, 3 * 4096
@@ -215,7 +222,8 @@ def kernel_rooflines(torch, peaks, lanes):
     out["attn3_core_L0"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                             "frac": flops / t / 1e12 / peaks["tf_burst"], "traffic": None, "flops_per_launch": flops,
                             "ms_per_launch": t * 1e3, "lanes": ql,
-                            "note": "d=40 is exp-bound: 128x128 exps/tile at 16 MUFU/clk/SM = 1024 clk vs 384 clk of MMA"}
+                            "note": "d=40: one 128x128 tile = 3 QK^T + 8 PV tcgen05.mma at ~160/~132 clk each = 1536 clk of tensor-pipe "
+                                    "issue time (math: 384 clk) vs 1024 clk of MUFU exp time: tensor-ISSUE bound, measured ~1700 clk/tile"}
     del xs, ys, q, k, v, o
     torch.cuda.empty_cache()
     return out
