@@ -22,9 +22,14 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 // GroupNorm
 // ------------------------------------------------------------------------------------------------
-constexpr int kGnMaxChunks = 32;
-__host__ __device__ inline int gn_chunks(int hw) {
-  int c = hw / 128;
+constexpr int kGnMaxChunks = 128;
+// pixel chunks per image (same split for the statistics and the apply pass): about one resident wave of blocks over
+// the whole launch (6 blocks x 148 SMs), at least 4 pixels per thread, so neither the per-block prologue/tail nor
+// a handful of fat blocks dominates
+static inline int gn_chunks(int hw, int n_img, int PS) {
+  int by_work = hw / (4 * PS);
+  int by_wave = (6 * num_sms() + n_img - 1) / n_img;
+  int c = by_work < by_wave ? by_work : by_wave;
   return c < 1 ? 1 : (c > kGnMaxChunks ? kGnMaxChunks : c);
 }
 // block = V * PS threads: V = C/8 channel vectors, PS pixel lanes
@@ -74,17 +79,27 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x0, int c0, const bf16*
     sm[(pl * C + v * 8 + i) * 2 + 1] = q[i];
   }
   __syncthreads();
-  const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    float ts = 0.f, tq = 0.f;
-    for (int pp = 0; pp < PS; ++pp)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        ts += sm[(pp * C + c) * 2 + 0];
-        tq += sm[(pp * C + c) * 2 + 1];
+  // one full warp per group: lanes stride over the (pixel lane, channel) partials, then a shuffle reduction
+  const int cpg = C / groups, items = PS * cpg;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, full_warps = blockDim.x >> 5;
+  if (warp < full_warps) {
+    for (int g = warp; g < groups; g += full_warps) {
+      float ts = 0.f, tq = 0.f;
+      for (int it = lane; it < items; it += 32) {
+        const int pp = it / cpg, c = g * cpg + it % cpg;
+        const float2 e = *reinterpret_cast<const float2*>(&sm[(pp * C + c) * 2]);
+        ts += e.x;
+        tq += e.y;
       }
-    float* dst = partial + ((static_cast<long long>(n) * chunks + chunk) * groups + g) * 2;
-    dst[0] = ts;
-    dst[1] = tq;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ts += __shfl_xor_sync(0xffffffffu, ts, o);
+        tq += __shfl_xor_sync(0xffffffffu, tq, o);
+      }
+      if (lane == 0)
+        *reinterpret_cast<float2*>(partial + ((static_cast<long long>(n) * chunks + chunk) * groups + g) * 2) =
+            make_float2(ts, tq);
+    }
   }
 }
 
@@ -93,22 +108,36 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x0, int c0, const bf16*
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                 bf16* __restrict__ y) {
   __shared__ float s_mean[64], s_rstd[64];
+  __shared__ float2 s_red[320];
   const int C = c0 + c1, V = C / 8, PS = blockDim.x / V;
   const int v = threadIdx.x % V, pl = threadIdx.x / V;
   const int n = blockIdx.y;
   const int cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    float ts = 0.f, tq = 0.f;
-    for (int ch = 0; ch < chunks; ++ch) {
-      const float* src = partial + ((static_cast<long long>(n) * chunks + ch) * groups + g) * 2;
-      ts += src[0];
-      tq += src[1];
+  {  // reduce the per-chunk partials: thread (row, g) sums chunks row, row + rows, ...; then rows are folded
+    const int rows_all = blockDim.x / groups, rows_cap = 320 / groups;
+    const int rows = rows_all < rows_cap ? rows_all : rows_cap, g = threadIdx.x % groups, row = threadIdx.x / groups;
+    if (row < rows) {
+      float ts = 0.f, tq = 0.f;
+      for (int ch = row; ch < chunks; ch += rows) {
+        const float2 e = *reinterpret_cast<const float2*>(partial + ((static_cast<long long>(n) * chunks + ch) * groups + g) * 2);
+        ts += e.x;
+        tq += e.y;
+      }
+      s_red[row * groups + g] = make_float2(ts, tq);
     }
-    const float cnt = static_cast<float>(hw) * cpg;
-    const float mean = ts / cnt;
-    const float var = fmaxf(tq / cnt - mean * mean, 0.f);
-    s_mean[g] = mean;
-    s_rstd[g] = rsqrtf(var + eps);
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      float ts = 0.f, tq = 0.f;
+      for (int r = 0; r < rows; ++r) {
+        ts += s_red[r * groups + threadIdx.x].x;
+        tq += s_red[r * groups + threadIdx.x].y;
+      }
+      const float cnt = static_cast<float>(hw) * cpg;
+      const float mean = ts / cnt;
+      const float var = fmaxf(tq / cnt - mean * mean, 0.f);
+      s_mean[threadIdx.x] = mean;
+      s_rstd[threadIdx.x] = rsqrtf(var + eps);
+    }
   }
   __syncthreads();
   const int slabs = gridDim.x, slab = blockIdx.x;
@@ -234,58 +263,71 @@ __global__ void timestep_features_kernel(const float* __restrict__ t, int n, int
   out[r * dim + half + i] = sinf(arg);
 }
 
-// out[r][m] = act_out( sum_k W[m][k] * act_in(x[r][k]) + b[m] ); one warp per kF consecutive output
-// features: the warp keeps its kF weight rows in registers (k <= 1280) and streams the n activation rows
-// once, so activations are re-read m/kF times instead of m times.
-constexpr int kSlF = 4;     // features per warp
-constexpr int kSlMaxV = 5;  // 16-byte weight vectors per lane per feature (k <= 32*8*5 = 1280)
+// out[r][m] = act_out( sum_k W[m][k] * act_in(x[r][k]) + b[m] ).  Block = 8 warps = 32 output features; every warp
+// keeps 4 weight rows in registers (k <= 1280) and the block streams the n activation rows through shared memory in
+// chunks of 8 rows (act_in applied once while staging), so x is read from L2 once per 32 features.
+// Element mapping inside a row: float4 index q = i*64 + h*32 + lane (i < 5, h < 2) -> conflict-free LDS.128.
+constexpr int kSlF = 4;      // features per warp
+constexpr int kSlWarps = 8;  // warps per block
+constexpr int kSlRows = 8;   // activation rows staged per chunk
 __global__ void small_linear_kernel(const float* __restrict__ x, int n, int k, const bf16* __restrict__ w,
                                     const float* __restrict__ b, int m, int silu_in, int silu_out,
                                     float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kSlF;
-  if (row0 >= m) return;
-  const int V = k / 8;
-  float wf[kSlF][kSlMaxV][8];
+  extern __shared__ float xs[];  // [kSlRows][k]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row0 = (blockIdx.x * kSlWarps + warp) * kSlF;
+  const int Q = k / 4;  // float4 per row
+  float wf[kSlF][5][2][4];
 #pragma unroll
   for (int f = 0; f < kSlF; ++f)
 #pragma unroll
-    for (int i = 0; i < kSlMaxV; ++i) {
-      const int v = lane + 32 * i;
-      if (row0 + f < m && v < V) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(w + static_cast<long long>(row0 + f) * k + v * 8)), wf[f][i]);
-      } else {
+    for (int i = 0; i < 5; ++i)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) wf[f][i][e] = 0.f;
-      }
-    }
-  for (int r = 0; r < n; ++r) {
-    float acc[kSlF];
-#pragma unroll
-    for (int f = 0; f < kSlF; ++f) acc[f] = 0.f;
-#pragma unroll
-    for (int i = 0; i < kSlMaxV; ++i) {
-      const int v = lane + 32 * i;
-      if (v < V) {
-        const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r) * k + v * 8));
-        const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r) * k + v * 8 + 4));
-        float xf[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float xv = silu_in ? silu_f(xf[e]) : xf[e];
-#pragma unroll
-          for (int f = 0; f < kSlF; ++f) acc[f] = fmaf(wf[f][i][e], xv, acc[f]);
+      for (int h = 0; h < 2; ++h) {
+        const int q = i * 64 + h * 32 + lane;
+        float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+        if (row0 + f < m && q < Q) {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(w + static_cast<long long>(row0 + f) * k + q * 4));
+          lo = unpack_bf16x2(raw.x);
+          hi = unpack_bf16x2(raw.y);
         }
+        wf[f][i][h][0] = lo.x; wf[f][i][h][1] = lo.y; wf[f][i][h][2] = hi.x; wf[f][i][h][3] = hi.y;
       }
+  for (int r0 = 0; r0 < n; r0 += kSlRows) {
+    const int rows = (n - r0) < kSlRows ? (n - r0) : kSlRows;
+    __syncthreads();  // previous chunk fully consumed
+    for (int idx = threadIdx.x; idx < rows * Q; idx += blockDim.x) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r0) * k) + idx);
+      if (silu_in) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+      reinterpret_cast<float4*>(xs)[idx] = v;
     }
+    __syncthreads();
+    if (row0 < m) {
+      for (int r = 0; r < rows; ++r) {
+        float acc[kSlF] = {0.f, 0.f, 0.f, 0.f};
+        const float4* xr = reinterpret_cast<const float4*>(xs + r * k);
 #pragma unroll
-    for (int f = 0; f < kSlF; ++f) {
-      float a = acc[f];
+        for (int i = 0; i < 5; ++i)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0 && row0 + f < m) {
-        const float y = a + (b ? b[row0 + f] : 0.f);
-        out[static_cast<long long>(r) * m + row0 + f] = silu_out ? silu_f(y) : y;
+          for (int h = 0; h < 2; ++h) {
+            const int q = i * 64 + h * 32 + lane;
+            if (q < Q) {
+              const float4 xv = xr[q];
+#pragma unroll
+              for (int f = 0; f < kSlF; ++f)
+                acc[f] = fmaf(wf[f][i][h][0], xv.x, fmaf(wf[f][i][h][1], xv.y, fmaf(wf[f][i][h][2], xv.z, fmaf(wf[f][i][h][3], xv.w, acc[f]))));
+            }
+          }
+#pragma unroll
+        for (int f = 0; f < kSlF; ++f) {
+          float a = acc[f];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+          if (lane == 0 && row0 + f < m) {
+            const float y = a + (b ? b[row0 + f] : 0.f);
+            out[static_cast<long long>(r0 + r) * m + row0 + f] = silu_out ? silu_f(y) : y;
+          }
+        }
       }
     }
   }
@@ -379,7 +421,7 @@ extern "C" int sg_groupnorm_stats(const void* x0, int32_t c0, const void* x1, in
   if (C % 8 || c0 % 8 || C % groups || groups > 64 || C / 8 > 1024) return SG_ERR_SHAPE;
   int V, PS;
   gn_block_shape(C, &V, &PS);
-  const int chunks = gn_chunks(hw);
+  const int chunks = gn_chunks(hw, n_img, PS);
   const size_t smem = static_cast<size_t>(PS) * C * 2 * sizeof(float);
   gn_stats_kernel<<<dim3(chunks, n_img), V * PS, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(x0), c0, static_cast<const bf16*>(x1), c1, hw, groups, stats);
@@ -394,10 +436,8 @@ extern "C" int sg_groupnorm_apply(const void* x0, int32_t c0, const void* x1, in
   if (C % 8 || c0 % 8 || C % groups || groups > 64 || C / 8 > 1024) return SG_ERR_SHAPE;
   int V, PS;
   gn_block_shape(C, &V, &PS);
-  const int chunks = gn_chunks(hw);
-  int slabs = hw / (PS * 4);
-  slabs = slabs < 1 ? 1 : (slabs > 64 ? 64 : slabs);
-  gn_apply_kernel<<<dim3(slabs, n_img), V * PS, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int chunks = gn_chunks(hw, n_img, PS);
+  gn_apply_kernel<<<dim3(chunks, n_img), V * PS, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(x0), c0, static_cast<const bf16*>(x1), c1, hw, groups, chunks, eps, stats, gamma,
       beta, silu, static_cast<bf16*>(y));
   SG_LAUNCH_END();
@@ -435,9 +475,10 @@ extern "C" int sg_timestep_features(const float* t, int32_t n, int32_t dim, floa
 extern "C" int sg_small_linear(const float* x, int32_t n, int32_t k, const void* w, const float* b, int32_t m,
                                int32_t silu_in, int32_t silu_out, float* out, void* stream) {
   if (!x || !w || !out) return SG_ERR_ARG;
-  if (k % 8 || k > 32 * 8 * kSlMaxV) return SG_ERR_SHAPE;
-  const int warps_needed = (m + kSlF - 1) / kSlF;
-  small_linear_kernel<<<(warps_needed + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (k % 8 || k > 1280) return SG_ERR_SHAPE;
+  const int feats_per_block = kSlWarps * kSlF;
+  const size_t smem = static_cast<size_t>(kSlRows) * k * sizeof(float);
+  small_linear_kernel<<<(m + feats_per_block - 1) / feats_per_block, kSlWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       x, n, k, static_cast<const bf16*>(w), b, m, silu_in, silu_out, out);
   SG_LAUNCH_END();
 }

@@ -93,13 +93,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       int mma_tile = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // the last N tile may be ragged (e.g. N = 640 as 256 + 256 + 128): issue only the columns that exist
+        const int nt_mma = tile % p.num_n_tiles;
+        const int ncols = (p.N - nt_mma * BN) < BN ? (p.N - nt_mma * BN) : BN;
+        const uint32_t idesc = make_idesc_bf16(kBM, static_cast<uint32_t>((ncols + 15) & ~15), 0, 0);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         if (p.dbg != nullptr && blockIdx.x == 0 && mma_tile < 8) p.dbg[(1 * 8 + mma_tile) * 8 + 0] = clock64();
@@ -230,7 +233,9 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
     if (rc != 0) return rc;
   }
 
-  const int bn_tile = (a->N % 256 == 0) ? 256 : ((a->N % 160 == 0) ? 160 : ((a->N % 128 == 0) ? 128 : 64));
+  // tile width: per tcgen05.mma the cost is ~128 + N/4 clk (profiles/r01_ubench_mma_cost.log), so 256-wide tiles with a
+  // ragged last tile beat 160-wide ones from N = 512 on (N = 640: 2 x 194 + 160 vs 4 x 167 clk per k-step)
+  const int bn_tile = (a->N % 256 == 0 || a->N >= 512) ? 256 : ((a->N % 160 == 0) ? 160 : ((a->N % 128 == 0) ? 128 : 64));
   {
     uint64_t dims[2] = {static_cast<uint64_t>(a->Ktot), static_cast<uint64_t>(a->N)};
     uint64_t strides[1] = {static_cast<uint64_t>(a->Ktot) * 2};

@@ -8,9 +8,9 @@ conv taps / shortcut / fused projections concatenated along K or N as the kernel
 Launch sequence per ResnetBlock2D (6 kernels):
     gn_stats, gn_apply+SiLU(+channel concat) -> conv3x3 GEMM (+bias +time embedding)
     gn_stats, gn_apply+SiLU                  -> conv3x3 GEMM (+1x1 shortcut as extra K segments | +x)
-per Transformer2DModel (feature pass 17, denoise pass 20 kernels):
+per Transformer2DModel (feature pass 16, denoise pass 19 kernels; + one text K/V GEMM per forward or per prompt):
     GN -> proj_in GEMM -> LN1 -> QKV GEMM -> attention -> out-proj GEMM(+h) [= the tapped feature]
-    LN2(/LN4) -> Q GEMM, text KV GEMM, attention [-> Q3 GEMM, image KV GEMM, attention]
+    LN2(/LN4) -> Q GEMM, attention over the pre-projected text K/V [-> Q3 GEMM, image KV GEMM, attention]
     out-proj GEMM over [a_text | a_image] (+2h)  -> LN3 -> FF1 GEMM(GEGLU) -> FF2 GEMM(+h) -> proj_out GEMM(+x)
 """
 from __future__ import annotations
@@ -90,7 +90,7 @@ class UNetEngine:
         d["w_qkv1"] = self._bf(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0))
         d["w_o1"], d["b_o1"] = self._bf(a1.to_out[0].weight), self._f32(a1.to_out[0].bias)
         d["w_q2"] = self._bf(a2.to_q.weight)
-        d["w_kv2"] = self._bf(torch.cat([a2.to_k.weight, a2.to_v.weight], 0))
+        d["w_kv2"] = torch.cat([a2.to_k.weight.detach(), a2.to_v.weight.detach()], 0)  # fused across layers in _pack
         d["w_o2"], d["b_o2"] = self._bf(a2.to_out[0].weight), self._f32(a2.to_out[0].bias)
         d["w_q3"] = self._bf(a3.to_q.weight)
         d["w_kv3"] = self._bf(torch.cat([a3.to_k.weight, a3.to_v.weight], 0))
@@ -139,6 +139,16 @@ class UNetEngine:
             else:
                 d["up"] = None
             self.up.append(d)
+        # attn2 to_k / to_v of all transformers as ONE weight [sum 2c, cross_attention_dim]: the text tokens do not
+        # change across denoising steps, so the pipeline projects them once per prompt (project_text)
+        order = [t for b in self.down if b["attn"] for t in b["attn"]] + self.mid["attn"] + \
+                [t for b in self.up if b["attn"] for t in b["attn"]]
+        off = 0
+        for t in order:
+            t["kv2_off"] = off
+            off += t["w_kv2"].shape[0]
+        self.w_kv2_all = self._bf(torch.cat([t.pop("w_kv2") for t in order], 0))
+        self.n_kv2 = off
         self.temb_w = self._bf(torch.cat(tw, 0))
         self.temb_b = self._f32(torch.cat(tb, 0))
         self.norm_out = (self._f32(m.conv_norm_out.weight), self._f32(m.conv_norm_out.bias))
@@ -186,8 +196,17 @@ class UNetEngine:
         ops.gemm(srcs, segs, (w, h, n), p["w2"], out, bias=p["b2"], residual=residual)
         return out
 
-    def _transformer(self, p, x, n, h, w, text, n_text_tokens, image, kv_map, n_kv_lanes):
-        """x (n, h, w, c); text (n * L, D) bf16; image None or (n_kv, R*hw, c) bf16.
+    def project_text(self, encoder_hidden_states, out=None):
+        """(n, L, D) text tokens -> (n * L, n_kv2) bf16: attn2 K | V of every transformer, layer l at columns
+        [kv2_off, kv2_off + 2c)  (model/attention.py:262 `to_k`/`to_v` of attn2, hoisted out of the step loop)."""
+        text = encoder_hidden_states.to(self.dev, BF16).contiguous()
+        n, L, d = text.shape
+        if out is None:
+            out = self._new(n * L, self.n_kv2)
+        return ops.linear(text.view(n * L, d), self.w_kv2_all, out)
+
+    def _transformer(self, p, x, n, h, w, text_kv, n_text_tokens, image, kv_map, n_kv_lanes):
+        """x (n, h, w, c); text_kv (n * L, n_kv2) bf16 from project_text; image None or (n_kv, R*hw, c) bf16.
         Returns (out (n, h, w, c), tap (n, hw, c))."""
         hw, c, heads, hd = h * w, p["c"], p["heads"], p["hd"]
         m = n * hw
@@ -214,10 +233,10 @@ class UNetEngine:
         q2 = self._new(m, c)
         ops.linear(n2, p["w_q2"], q2)
         L = n_text_tokens
-        kv2 = self._new(n * L, 2 * c)
-        ops.linear(text, p["w_kv2"], kv2)
+        ld = text_kv.shape[1]
+        kv2 = text_kv[:, p["kv2_off"]:]
         a2 = self._new(m, c)
-        ops.attention(q2, kv2, kv2[:, c:], a2, n, heads, hd, hw, L, (hw * c, c), (L * 2 * c, 2 * c), (L * 2 * c, 2 * c))
+        ops.attention(q2, kv2, kv2[:, c:], a2, n, heads, hd, hw, L, (hw * c, c), (L * ld, ld), (L * ld, ld))
         h2 = self._new(m, c)
         if image is not None:
             q3 = self._new(m, c)
@@ -266,7 +285,8 @@ class UNetEngine:
     # forward
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, sample, timestep, encoder_hidden_states, image_hidden_states=None, kv_map=None):
+    def forward(self, sample, timestep, encoder_hidden_states, image_hidden_states=None, kv_map=None, text_kv=None):
+        """text_kv: optional result of project_text(encoder_hidden_states) (cached across steps by the pipeline)."""
         dev = self.dev
         n, _, h, w = sample.shape
         if (h % (1 << self.model.num_upsamplers)) or (w % (1 << self.model.num_upsamplers)):
@@ -284,7 +304,10 @@ class UNetEngine:
             raise ValueError(f"encoder_hidden_states {tuple(text3.shape)} does not match batch {n} / "
                              f"cross_attention_dim {self.model.config.cross_attention_dim}")
         L = text3.shape[1]
-        text = text3.view(n * L, -1)
+        if text_kv is None:
+            text_kv = self.project_text(text3)
+        elif tuple(text_kv.shape) != (n * L, self.n_kv2):
+            raise ValueError(f"text_kv has shape {tuple(text_kv.shape)}, expected {(n * L, self.n_kv2)}")
         img = None
         if image_hidden_states is not None:
             img = {k: v.to(dev, BF16).contiguous() for k, v in image_hidden_states.items()}
@@ -315,7 +338,7 @@ class UNetEngine:
                                      f"(lanes, R*{hh * ww}, {p['c']})")
                 if kv_map is None and image.shape[0] != n:
                     raise ValueError(f"image_hidden_states[{key!r}] has {image.shape[0]} lanes for a batch of {n}")
-            out, tap = self._transformer(p, x, n, hh, ww, text, L, image, kv_map, 0)
+            out, tap = self._transformer(p, x, n, hh, ww, text_kv, L, image, kv_map, 0)
             if img is None:
                 taps[key] = tap
             return out

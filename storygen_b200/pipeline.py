@@ -66,6 +66,9 @@ class _DenoiseLoop:
         self.f_noisy = torch.empty(nf, *lat_shape, dtype=F32, device=dev)
         self.m_text = torch.empty(3, B, *text_shape, dtype=torch.bfloat16, device=dev)
         self.lat3 = torch.empty(3 * B, *lat_shape, dtype=F32, device=dev)
+        # attn2 K/V of every layer for the text lanes: projected once per load(), reused by all steps
+        self.f_kv = torch.empty(nf * text_shape[0], self.eng.n_kv2, dtype=torch.bfloat16, device=dev)
+        self.m_kv = torch.empty(3 * B * text_shape[0], self.eng.n_kv2, dtype=torch.bfloat16, device=dev)
         # denoise lane (g3, b): g3 = 0 -> K/V lane b (zero frame); g3 = 1, 2 -> K/V lane B + b
         self.kv_map = torch.tensor([b for b in range(B)] + [B + b for b in range(B)] * 2, dtype=torch.int32, device=dev)
         self.acp = scheduler.alphas_cumprod.to(dev, F32).contiguous()
@@ -101,16 +104,20 @@ class _DenoiseLoop:
         self.m_text[0].copy_(text_uncond, **nb)
         self.m_text[1].copy_(text_uncond, **nb)
         self.m_text[2].copy_(text_cond, **nb)
+        self.eng.project_text(self.f_text.view(self.nf, *self.f_text.shape[3:]), out=self.f_kv)
+        self.eng.project_text(self.m_text.view(3 * self.B, *self.m_text.shape[2:]), out=self.m_kv)
+        self.kernel_launches += 2
 
     def _step_body(self):
         nf, B = self.nf, self.B
         lat_shape = self.latents.shape[1:]
         ops.add_noise(self.f_src.view(nf, *lat_shape), self.f_eps.view(nf, *lat_shape), self.acp, self.par_i, self.f_noisy)
-        taps = self.eng.forward(self.f_noisy, self.par[:nf], self.f_text.view(nf, *self.f_text.shape[3:]), None)[1]
+        taps = self.eng.forward(self.f_noisy, self.par[:nf], self.f_text.view(nf, *self.f_text.shape[3:]), None,
+                                text_kv=self.f_kv)[1]
         cond = {k: v.view(2 * B, -1, v.shape[-1]) for k, v in taps.items()}
         self.lat3.view(3, B, -1).copy_(self.latents.view(1, B, -1).expand(3, B, -1))
         eps3 = self.eng.forward(self.lat3, self.par[nf:nf + 3 * B], self.m_text.view(3 * B, *self.m_text.shape[2:]), cond,
-                                kv_map=self.kv_map)[0]
+                                kv_map=self.kv_map, text_kv=self.m_kv)[0]
         ops.cfg_ddim_step(eps3, self.latents, self.s_img, self.s_txt, self.par[nf + 3 * B:])
 
     def run(self, use_cuda_graph: bool = True, callback=None, callback_steps: int = 1):
