@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
   uint64_t* s_free = o_done + 2;         // [2] softmax -> MMA (S row-blocks are in registers; kSepP only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // broadcast: provably warp-uniform role index
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (128 * QT);
   const int head = blockIdx.y;
@@ -111,32 +111,32 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for the compiler
 
   if (warp < Cfg::kFirstSoftmaxWarp) {
   // register re-distribution between warpgroups (QT == 2): warpgroup 0 = {TMA, MMA, 2 idle warps} gives its
   // registers to the 8 softmax warps, which hold a 128-wide S row per thread
   if constexpr (QT == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0) {
-    // ===================== TMA loader =====================
-    if (lane == 0) {
+    // ===================== TMA loader (whole warp; one elected lane issues, see ptx.cuh) =====================
+    {
       const int kv_img = (p.kv_map != nullptr) ? p.kv_map[img] : img;
 #pragma unroll
       for (int t = 0; t < QT; ++t) {
-        mbar_arrive_expect_tx(&q_full[t], Cfg::kTileBytes);
+        mbar_arrive_expect_tx_w(&q_full[t], Cfg::kTileBytes);
 #pragma unroll
         for (int a = 0; a < NA; ++a)
-          tma_load_3d(q_smem + t * Cfg::kTileBytes + a * kAtomBytes, &p.q_map, &q_full[t], head * D + 64 * a,
+          tma_load_3d_w(q_smem + t * Cfg::kTileBytes + a * kAtomBytes, &p.q_map, &q_full[t], head * D + 64 * a,
                       q0 + 128 * t, img);
       }
       int slot = 0;
       uint32_t phase = 0;
       auto load_tile = [&](const CUtensorMap* map, int key0) {
         mbar_wait(&kv_empty[slot], phase ^ 1);
-        mbar_arrive_expect_tx(&kv_full[slot], Cfg::kTileBytes);
+        mbar_arrive_expect_tx_w(&kv_full[slot], Cfg::kTileBytes);
 #pragma unroll
         for (int a = 0; a < NA; ++a)
-          tma_load_3d(kv_smem + slot * Cfg::kTileBytes + a * kAtomBytes, map, &kv_full[slot], head * D + 64 * a,
+          tma_load_3d_w(kv_smem + slot * Cfg::kTileBytes + a * kAtomBytes, map, &kv_full[slot], head * D + 64 * a,
                       key0, kv_img);
         if (++slot == kSlots) {
           slot = 0;
@@ -157,16 +157,16 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == 1 || (Cfg::kSepP && warp == 2)) {
+    // ===================== MMA issuer(s) (whole warp; one elected lane issues) =====================
+    {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
       auto qk = [&](uint32_t q_addr, uint32_t k_addr, uint32_t s_col) {
 #pragma unroll
         for (int ks = 0; ks < Cfg::KQ; ++ks) {
           const uint32_t off = (ks >> 2) * kAtomBytes + (ks & 3) * 32;
-          umma_ss(tmem_base + s_col, make_smem_desc(q_addr + off, 16, 1024, kLayoutSW128),
+          umma_ss_w(tmem_base + s_col, make_smem_desc(q_addr + off, 16, 1024, kLayoutSW128),
                   make_smem_desc(k_addr + off, 16, 1024, kLayoutSW128), idesc_qk, ks != 0);
         }
       };
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             // V tile rows = keys (128 B pitch); 16 keys per k-step = 2048 B
-            umma_ts(tmem_base + o_col + 64 * a, tmem_base + p_col + ks * 8,
+            umma_ts_w(tmem_base + o_col + 64 * a, tmem_base + p_col + ks * 8,
                     make_smem_desc(v_addr + a * kAtomBytes + ks * 2048, kAtomBytes, 1024, kLayoutSW128), idesc_pv,
                     !(first && ks == 0));
           }
@@ -190,8 +190,8 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
           mbar_wait(&kv_full[slot], phase);
           tc_fence_after();
           qk(q_addr, smem_u32(kv_smem + slot * Cfg::kTileBytes), (j & 1) * 128);
-          umma_commit(&kv_empty[slot]);
-          umma_commit(&s_full[j & 1]);
+          umma_commit_w(&kv_empty[slot]);
+          umma_commit_w(&s_full[j & 1]);
           if (++slot == kSlots) {
             slot = 0;
             phase ^= 1;
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
           mbar_wait(&kv_full[slot], phase);
           tc_fence_after();
           pv((j & 1) * 128, smem_u32(kv_smem + slot * Cfg::kTileBytes), Cfg::kColO, j == 0);
-          umma_commit(&kv_empty[slot]);
-          umma_commit(&o_done[0]);
+          umma_commit_w(&kv_empty[slot]);
+          umma_commit_w(&o_done[0]);
           if (++slot == kSlots) {
             slot = 0;
             phase ^= 1;
@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
           mbar_wait(&q_ready[t], 0);
           tc_fence_after();
           qk(smem_u32(q_smem + t * Cfg::kTileBytes), tile_addr(0), t * 128);
-          umma_commit(&s_full[t]);
+          umma_commit_w(&s_full[t]);
         }
-        umma_commit(&kv_empty[slot_of(0)]);
+        umma_commit_w(&kv_empty[slot_of(0)]);
         for (int j = 0; j < T; ++j) {
           const int iv = 2 * j + 1, ik = 2 * j + 2;
           const bool more = (j + 1 < T);
@@ -236,60 +236,52 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
             mbar_wait(&p_full[t], j & 1);
             tc_fence_after();
             pv(t * 128, tile_addr(iv), Cfg::kColO + t * 64 * NA, j == 0);
-            umma_commit(&o_done[t]);
+            umma_commit_w(&o_done[t]);
             if (more) {
               qk(smem_u32(q_smem + t * Cfg::kTileBytes), tile_addr(ik), t * 128);
-              umma_commit(&s_full[t]);
+              umma_commit_w(&s_full[t]);
             }
           }
-          umma_commit(&kv_empty[slot_of(iv)]);
-          if (more) umma_commit(&kv_empty[slot_of(ik)]);
+          umma_commit_w(&kv_empty[slot_of(iv)]);
+          if (more) umma_commit_w(&kv_empty[slot_of(ik)]);
         }
       } else {
-        // Event-driven issue (kSepP): per query tile t two independent streams,
-        //   QK_t(j) as soon as K_j has landed and the softmax warps have read S_t(j-1)   [s_free]
-        //   PV_t(j) as soon as V_j has landed and P_t(j) is published                    [p_full]
-        // polled round-robin with non-blocking mbarrier tests.  Every barrier phase is tested only after
-        // the previous phase of that barrier was seen complete (parity waits are only valid in order).
+        // kSepP: TWO issuing threads, one in-order stream each (warp 1: Q K^T, warp 2: P V).  A shared-memory
+        // operation of the issuing thread (mbarrier test, LDS) right after a tcgen05.mma costs ~100 clk
+        // (profiles/r01_ubench_issue_stream.log), so one thread polling four event sources starved the tensor
+        // pipe; two blocking streams need one wait per 3 / 8 MMAs and overlap each other.
+        //   QK_t(j): K_j landed, softmax warps have read S_t(j-1) [s_free];  PV_t(j): V_j landed, P_t(j) published
         auto slot_of = [](int i) { return i % kSlots; };
         auto phase_of = [](int i) { return static_cast<uint32_t>((i / kSlots) & 1); };
         auto tile_addr = [&](int i) { return smem_u32(kv_smem + slot_of(i) * Cfg::kTileBytes); };
-        int qk_next[2] = {0, 0}, pv_next[2] = {0, 0};
-        uint32_t spins = 0;
-        while (pv_next[0] < T || pv_next[1] < T) {
-          bool progress = false;
+        if (warp == 1) {
+          for (int j = 0; j < T; ++j) {
+            const int ik = 2 * j;
+            mbar_wait(&kv_full[slot_of(ik)], phase_of(ik));
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            if (qk_next[t] < T) {
-              const int j = qk_next[t], ik = 2 * j;
-              const bool s_ok = (j == 0) ? mbar_test(&q_ready[t], 0) : mbar_test(&s_free[t], (j - 1) & 1);
-              if (s_ok && mbar_test(&kv_full[slot_of(ik)], phase_of(ik))) {
-                tc_fence_after();
-                if (dbg_on && j < 16) p.dbg[(1 * 16 + j) * 8 + t * 2] = clock64();
-                qk(smem_u32(q_smem + t * Cfg::kTileBytes), tile_addr(ik), t * 128);
-                umma_commit(&s_full[t]);
-                qk_next[t] = j + 1;
-                if (qk_next[1 - t] > j) umma_commit(&kv_empty[slot_of(ik)]);  // both tiles have used K_j
-                progress = true;
-              }
+            for (int t = 0; t < 2; ++t) {
+              if (j == 0) mbar_wait(&q_ready[t], 0);
+              else mbar_wait(&s_free[t], (j - 1) & 1);
+              tc_fence_after();
+              if (dbg_on && lane == 0 && j < 16) p.dbg[(1 * 16 + j) * 8 + t * 2] = clock64();
+              qk(smem_u32(q_smem + t * Cfg::kTileBytes), tile_addr(ik), t * 128);
+              umma_commit_w(&s_full[t]);
             }
-            if (pv_next[t] < T) {
-              const int j = pv_next[t], iv = 2 * j + 1;
-              if (mbar_test(&p_full[t], j & 1) && mbar_test(&kv_full[slot_of(iv)], phase_of(iv))) {
-                tc_fence_after();
-                if (dbg_on && j < 16) p.dbg[(1 * 16 + j) * 8 + t * 2 + 1] = clock64();
-                pv(Cfg::kColP + t * 64, tile_addr(iv), Cfg::kColO + t * 64, j == 0);
-                umma_commit(&o_done[t]);
-                pv_next[t] = j + 1;
-                if (pv_next[1 - t] > j) umma_commit(&kv_empty[slot_of(iv)]);  // both tiles have used V_j
-                progress = true;
-              }
-            }
+            umma_commit_w(&kv_empty[slot_of(ik)]);  // both tiles have used K_j
           }
-          if (progress) {
-            spins = 0;
-          } else if (++spins > (1u << 24)) {
-            __trap();  // lost arrive: fail loudly instead of hanging
+        } else {
+          for (int j = 0; j < T; ++j) {
+            const int iv = 2 * j + 1;
+            mbar_wait(&kv_full[slot_of(iv)], phase_of(iv));
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              mbar_wait(&p_full[t], j & 1);
+              tc_fence_after();
+              if (dbg_on && lane == 0 && j < 16) p.dbg[(1 * 16 + j) * 8 + t * 2 + 1] = clock64();
+              pv(Cfg::kColP + t * 64, tile_addr(iv), Cfg::kColO + t * 64, j == 0);
+              umma_commit_w(&o_done[t]);
+            }
+            umma_commit_w(&kv_empty[slot_of(iv)]);  // both tiles have used V_j
           }
         }
       }

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // broadcast: the compiler treats it as warp-uniform
   const int lane = threadIdx.x & 31;
   const int num_m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   const int num_tiles = num_m_tiles * p.num_n_tiles;
@@ -56,82 +56,76 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for the compiler
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      tma_prefetch_desc(&p.b_map);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.num_n_tiles;
-        const int nt = tile - mt * p.num_n_tiles;
-        const int tx = mt % p.tiles_x;
-        const int ty = (mt / p.tiles_x) % p.tiles_y;
-        const int tn = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
-        int kb = 0;
-        for (int s = 0; s < p.num_segs; ++s) {
-          const sg_seg seg = p.segs[s];
-          const CUtensorMap* amap = &p.a_maps[seg.src];
-          for (int j = 0; j < seg.nkb; ++j, ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_4d(smem_a + stage * Cfg::kABytes, amap, &full_bar[stage], seg.c0 + j * kBK,
-                        x0 + seg.dx, y0 + seg.dy, n0);
-            tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * kBK,
-                        nt * BN);
-            if (++stage == Cfg::kStages) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      int mma_tile = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        // the last N tile may be ragged (e.g. N = 640 as 256 + 256 + 128): issue only the columns that exist
-        const int nt_mma = tile % p.num_n_tiles;
-        const int ncols = (p.N - nt_mma * BN) < BN ? (p.N - nt_mma * BN) : BN;
-        const uint32_t idesc = make_idesc_bf16(kBM, static_cast<uint32_t>((ncols + 15) & ~15), 0, 0);
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        if (p.dbg != nullptr && blockIdx.x == 0 && mma_tile < 8) p.dbg[(1 * 8 + mma_tile) * 8 + 0] = clock64();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.total_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
-          const uint64_t a_desc = make_smem_desc(a_addr, 16, 1024, kLayoutSW128);
-          const uint64_t b_desc = make_smem_desc(b_addr, 16, 1024, kLayoutSW128);
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (>>4) address field
-            umma_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          }
-          umma_commit(&empty_bar[stage]);
+    // ===================== TMA producer (whole warp, one elected lane issues: see ptx.cuh) =====================
+    if (lane == 0) tma_prefetch_desc(&p.b_map);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.num_n_tiles;
+      const int nt = tile - mt * p.num_n_tiles;
+      const int tx = mt % p.tiles_x;
+      const int ty = (mt / p.tiles_x) % p.tiles_y;
+      const int tn = mt / (p.tiles_x * p.tiles_y);
+      const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+      int kb = 0;
+      for (int s = 0; s < p.num_segs; ++s) {
+        const sg_seg seg = p.segs[s];
+        const CUtensorMap* amap = &p.a_maps[seg.src];
+        for (int j = 0; j < seg.nkb; ++j, ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx_w(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d_w(smem_a + stage * Cfg::kABytes, amap, &full_bar[stage], seg.c0 + j * kBK, x0 + seg.dx,
+                        y0 + seg.dy, n0);
+          tma_load_2d_w(smem_b + stage * Cfg::kBBytes, &p.b_map, &full_bar[stage], kb * kBK, nt * BN);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);
-        if (p.dbg != nullptr && blockIdx.x == 0 && mma_tile < 8) p.dbg[(1 * 8 + mma_tile) * 8 + 1] = clock64();
-        ++mma_tile;
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int mma_tile = 0;
+    const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // the last N tile may be ragged (e.g. N = 640 as 256 + 256 + 128): issue only the columns that exist
+      const int nt_mma = tile % p.num_n_tiles;
+      const int ncols = (p.N - nt_mma * BN) < BN ? (p.N - nt_mma * BN) : BN;
+      const uint32_t idesc = make_idesc_bf16(kBM, static_cast<uint32_t>((ncols + 15) & ~15), 0, 0);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && mma_tile < 8) p.dbg[(1 * 8 + mma_tile) * 8 + 0] = clock64();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < p.total_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t a_desc = make_smem_desc(a_addr0 + stage * Cfg::kABytes, 16, 1024, kLayoutSW128);
+        const uint64_t b_desc = make_smem_desc(b_addr0 + stage * Cfg::kBBytes, 16, 1024, kLayoutSW128);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (>>4) address field
+          umma_ss_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
         }
+        umma_commit_w(&empty_bar[stage]);
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit_w(&tfull_bar[acc]);
+      if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && mma_tile < 8) p.dbg[(1 * 8 + mma_tile) * 8 + 1] = clock64();
+      ++mma_tile;
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else {

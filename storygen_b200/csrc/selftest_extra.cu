@@ -106,12 +106,18 @@ static void run_attn_case(const char* name, int D, int H, int n_lanes, int n_kv_
 void test_ubench();
 void test_ubench_mma();
 void test_ubench_cp();
+void test_ubench_mma_multi();
+void test_ubench_mma_var();
+void test_ubench_tma();
 void test_timeline();
 void test_gemm_timeline();
 void test_extra() {
   test_ubench();
   test_ubench_mma();
   test_ubench_cp();
+  test_ubench_mma_multi();
+  test_ubench_mma_var();
+  test_ubench_tma();
   test_timeline();
   test_gemm_timeline();
   run_attn_case("attn d40 self 2x8 nq=nk=256", 40, 8, 2, 2, 256, 256, 1.f, false, {});
@@ -132,6 +138,7 @@ void test_extra() {
 // ---------------------------------------------------------------------------------------------
 // micro-benchmarks (./selftest "ubench"): TMEM read throughput, MUFU.EX2 throughput
 // ---------------------------------------------------------------------------------------------
+#include "common.cuh"
 #include "ptx.cuh"
 __global__ void ubench_tmem_ld(int iters, long long* cycles, float* sink) {
   __shared__ uint32_t slot;
@@ -327,6 +334,215 @@ void test_ubench_mma() {
   run_mma_bench<160>(cyc);
   run_mma_bench<256>(cyc);
   cudaFree(cyc);
+}
+
+// does the ~130 clk per-instruction floor belong to the issuing thread or to the tensor pipe?  `issuers` warps of one
+// CTA (lane 0 of each) issue independent MMA streams into their own accumulators; optionally 2 CTAs per SM.
+template <int M, int N>
+__global__ void ubench_mma_multi(int iters, int issuers, int use_ts, long long* cycles) {
+  extern __shared__ uint8_t smem_raw_u[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_u) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) sg::mbar_init(&bar[i], 1); sg::fence_barrier_init(); }
+  sg::fence_proxy_async_smem();
+  if (threadIdx.x < 32) sg::tmem_alloc(&slot, 256);
+  sg::tc_fence_before();
+  __syncthreads();
+  sg::tc_fence_after();
+  const int warp = threadIdx.x >> 5;
+  long long t0 = 0, t1 = 0;
+  if (warp < issuers && (threadIdx.x & 31) == 0) {
+    const uint32_t idesc = sg::make_idesc_bf16(M, N, 0, 0);
+    const uint64_t a_desc = sg::make_smem_desc(sg::smem_u32(smem), 16, 1024, sg::kLayoutSW128);
+    const uint64_t b_desc = sg::make_smem_desc(sg::smem_u32(smem + 16384), 16, 1024, sg::kLayoutSW128);
+    const uint32_t d = slot + static_cast<uint32_t>(warp) * 64u;  // N <= 64 per issuer when issuers > 1
+    t0 = clock64();
+#pragma unroll 8
+    for (int it = 0; it < iters; ++it) {
+      const uint64_t koff = 2 * (it & 3);
+      if (use_ts) sg::umma_ts(d, slot + 192 + 16 * warp, b_desc + koff, idesc, 1);
+      else sg::umma_ss(d, a_desc + koff, b_desc + koff, idesc, 1);
+    }
+    sg::umma_commit(&bar[warp]);
+    sg::mbar_wait(&bar[warp], 0);
+    t1 = clock64();
+    if (warp == 0) cycles[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) sg::tmem_dealloc(slot, 256);
+}
+template <int M, int N>
+static void run_mma_multi(long long* cyc, int issuers, int ctas_per_sm, int ts) {
+  CK(cudaFuncSetAttribute(ubench_mma_multi<M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024));
+  const int iters = 512;
+  ubench_mma_multi<M, N><<<148 * ctas_per_sm, 128, 60 * 1024>>>(iters, issuers, ts, cyc);
+  CK(cudaDeviceSynchronize());
+  long long h;
+  CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+  printf("[ubench] tcgen05.mma M%-3d N%-3d K16 %s: %d issuing warp(s) x %d CTA/SM: %.1f clk per MMA per issuer -> %.1f clk per MMA per SM\n",
+         M, N, ts ? "TS" : "SS", issuers, ctas_per_sm, static_cast<double>(h) / iters,
+         static_cast<double>(h) / iters / (issuers * ctas_per_sm));
+}
+void test_ubench_mma_multi() {
+  if (!want("ubench")) return;
+  long long* cyc;
+  CK(cudaMalloc(&cyc, 8 * 1024));
+  for (int ts = 0; ts < 2; ++ts) {
+    run_mma_multi<128, 64>(cyc, 1, 1, ts);
+    run_mma_multi<128, 64>(cyc, 2, 1, ts);
+    run_mma_multi<128, 64>(cyc, 4, 1, ts);
+    run_mma_multi<128, 64>(cyc, 1, 2, ts);
+    run_mma_multi<128, 64>(cyc, 2, 2, ts);
+    run_mma_multi<128, 16>(cyc, 1, 1, ts);
+    run_mma_multi<128, 32>(cyc, 1, 1, ts);
+    run_mma_multi<64, 64>(cyc, 1, 1, ts);
+    run_mma_multi<64, 64>(cyc, 2, 1, ts);
+    run_mma_multi<64, 256>(cyc, 1, 1, ts);
+    run_mma_multi<128, 256>(cyc, 1, 1, ts);
+    run_mma_multi<128, 128>(cyc, 1, 2, ts);
+  }
+  cudaFree(cyc);
+}
+
+// what slows an MMA issue stream down?  V: 0 SS plain | 1 TS with the A address hoisted | 2 SS, accumulator address
+// re-read from shared memory every MMA | 3 SS + mbarrier.test_wait every 4 MMAs | 4 SS + tcgen05.commit every 4 MMAs
+// | 5 = 3 + 4 | 6 TS hoisted + commit every 8 + test_wait every 8
+template <int N, int V>
+__global__ void ubench_mma_var(int iters, long long* cycles) {
+  extern __shared__ uint8_t smem_raw_u[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_u) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t bar, bar2, bar3;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { sg::mbar_init(&bar, 1); sg::mbar_init(&bar2, 1); sg::mbar_init(&bar3, 1); sg::fence_barrier_init(); }
+  sg::fence_proxy_async_smem();
+  if (threadIdx.x < 32) sg::tmem_alloc(&slot, 512);
+  sg::tc_fence_before();
+  __syncthreads();
+  sg::tc_fence_after();
+  if (threadIdx.x == 0) {
+    sg::mbar_arrive(&bar3);  // phase 0 of bar3 is complete: test_wait(bar3, 0) returns true at once
+    const uint32_t idesc = sg::make_idesc_bf16(128, N, 0, 0);
+    const uint64_t a_desc = sg::make_smem_desc(sg::smem_u32(smem), 16, 1024, sg::kLayoutSW128);
+    const uint64_t b_desc = sg::make_smem_desc(sg::smem_u32(smem + 16384), 16, 1024, sg::kLayoutSW128);
+    const uint32_t d0 = slot, a_t = slot + 256;
+    uint32_t sink = 0;
+    const long long t0 = clock64();
+#pragma unroll 8
+    for (int it = 0; it < iters; ++it) {
+      const uint64_t koff = 2 * (it & 3);
+      if (V == 1 || V == 6) sg::umma_ts(d0, a_t, b_desc + koff, idesc, 1);
+      else if (V == 2) sg::umma_ss(*reinterpret_cast<volatile uint32_t*>(&slot), a_desc + koff, b_desc + koff, idesc, 1);
+      else sg::umma_ss(d0, a_desc + koff, b_desc + koff, idesc, 1);
+      if ((V == 3 || V == 5) && (it & 3) == 3) sink += sg::mbar_test(&bar3, 0) ? 1u : 0u;
+      if ((V == 4 || V == 5) && (it & 3) == 3) sg::umma_commit(&bar2);
+      if (V == 6 && (it & 7) == 7) { sg::umma_commit(&bar2); sink += sg::mbar_test(&bar3, 0) ? 1u : 0u; }
+    }
+    sg::umma_commit(&bar);
+    sg::mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0 + (sink == 0xffffffffu ? 1 : 0);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) sg::tmem_dealloc(slot, 512);
+}
+template <int N, int V>
+static void run_mma_var(long long* cyc, const char* what) {
+  CK(cudaFuncSetAttribute(ubench_mma_var<N, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024));
+  const int iters = 512;
+  ubench_mma_var<N, V><<<148, 128, 60 * 1024>>>(iters, cyc);
+  CK(cudaDeviceSynchronize());
+  long long h;
+  CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+  printf("[ubench] issue-stream N%-3d %-52s: %.1f clk per MMA (math %.0f)\n", N, what, static_cast<double>(h) / iters, N / 2.0);
+}
+template <int N>
+static void run_mma_vars(long long* cyc) {
+  run_mma_var<N, 0>(cyc, "SS plain");
+  run_mma_var<N, 1>(cyc, "TS, A address hoisted");
+  run_mma_var<N, 2>(cyc, "SS, D address re-read from smem per MMA");
+  run_mma_var<N, 3>(cyc, "SS + mbarrier.test_wait every 4");
+  run_mma_var<N, 4>(cyc, "SS + tcgen05.commit every 4");
+  run_mma_var<N, 5>(cyc, "SS + commit + test_wait every 4");
+  run_mma_var<N, 6>(cyc, "TS hoisted + commit + test_wait every 8");
+}
+void test_ubench_mma_var() {
+  if (!want("ubench2")) return;
+  long long* cyc;
+  CK(cudaMalloc(&cyc, 8 * 1024));
+  run_mma_vars<64>(cyc);
+  run_mma_vars<128>(cyc);
+  run_mma_vars<160>(cyc);
+  run_mma_vars<256>(cyc);
+  cudaFree(cyc);
+}
+
+// how many bytes per clock can one SM pull into shared memory with TMA?  A ring of 4 x 32 KB stages ([256 rows x 64
+// bf16] boxes of a row-major matrix), a consumer that frees a stage as soon as it lands, no tensor work at all.
+__global__ void ubench_tma_ingest(const __grid_constant__ CUtensorMap map, int rows_total, int iters, int spread,
+                                  long long* cycles) {
+  extern __shared__ uint8_t smem_raw_u[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_u) + 1023) & ~static_cast<uintptr_t>(1023));
+  __shared__ uint64_t full[4], empty[4];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) { sg::mbar_init(&full[i], 1); sg::mbar_init(&empty[i], 1); }
+    sg::fence_barrier_init();
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    const long long t0 = clock64();
+    // spread = 1: every CTA walks its own region (HBM stream); 0: all CTAs walk the same 8 MB (L2 hits)
+    int row = spread ? static_cast<int>((static_cast<long long>(blockIdx.x) * 8192) % rows_total) : (blockIdx.x * 256) % 8192;
+    for (int it = 0; it < iters; ++it) {
+      const int st = it & 3;
+      sg::mbar_wait(&empty[st], ((it >> 2) & 1) ^ 1);
+      sg::mbar_arrive_expect_tx(&full[st], 32768);
+      sg::tma_load_2d(smem + st * 32768, &map, &full[st], 0, row);
+      row += 256;
+      if (spread) { if (row >= rows_total) row = 0; } else if (row >= 65536) row = 0;
+    }
+    sg::mbar_wait(&full[(iters - 1) & 3], ((iters - 1) >> 2) & 1);  // last stage has landed
+    cycles[blockIdx.x] = clock64() - t0;
+  } else if (warp == 1 && lane == 0) {
+    for (int it = 0; it < iters; ++it) {
+      const int st = it & 3;
+      sg::mbar_wait(&full[st], (it >> 2) & 1);
+      sg::mbar_arrive(&empty[st]);
+    }
+  }
+}
+void test_ubench_tma() {
+  if (!want("ubench3")) return;
+  const int rows_total = 1 << 21;  // x 128 B = 256 MB
+  void* buf;
+  CK(cudaMalloc(&buf, static_cast<size_t>(rows_total) * 128));
+  CK(cudaMemset(buf, 0, static_cast<size_t>(rows_total) * 128));
+  CUtensorMap map;
+  uint64_t dims[2] = {64, static_cast<uint64_t>(rows_total)};
+  uint64_t strides[1] = {128};
+  uint32_t box[2] = {64, 256};
+  if (sg::encode_tmap_bf16(&map, buf, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) != 0) { printf("tmap failed\n"); return; }
+  long long* cyc;
+  CK(cudaMalloc(&cyc, 8 * 1024));
+  CK(cudaFuncSetAttribute(ubench_tma_ingest, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768 + 1024));
+  const int iters = 2048;
+  for (int spread = 0; spread < 2; ++spread)
+    for (int ctas : {1, 16, 74, 148}) {
+      ubench_tma_ingest<<<ctas, 64, 4 * 32768 + 1024>>>(map, rows_total, iters, spread, cyc);
+      CK(cudaDeviceSynchronize());
+      long long h[148];
+      CK(cudaMemcpy(h, cyc, 8 * ctas, cudaMemcpyDeviceToHost));
+      double mx = 0;
+      for (int i = 0; i < ctas; ++i) mx = h[i] > mx ? h[i] : mx;
+      printf("[ubench] TMA ingest, %3d CTAs (1/SM), %s: %.1f B/clk/SM (slowest CTA), aggregate %.2f TB/s @1.96 GHz\n", ctas,
+             spread ? "distinct regions (HBM)" : "shared 8 MB (L2)      ", 32768.0 * iters / mx,
+             32768.0 * iters / mx * ctas * 1.96e9 / 1e12);
+    }
+  cudaFree(cyc);
+  cudaFree(buf);
 }
 
 // TS-mode GEMM feasibility: per k-block 4 x tcgen05.cp (smem A [128 x 16] -> TMEM, 128x256b) + 4 x TS MMA
