@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libstorygen_b200.so")
+# STORYGEN_B200_LIB: developer override for A/B runs of an alternative in-tree build of the same library
+LIB_PATH = os.environ.get("STORYGEN_B200_LIB") or os.path.join(_HERE, "libstorygen_b200.so")
 
 SG_ABI_VERSION = 7
 SG_MAX_SRC = 4

@@ -23,6 +23,14 @@
 namespace sg {
 
 constexpr int kAtomBytes = 128 * 128;  // [128 rows x 64 bf16], swizzle 128B
+#ifndef SG_ATTN_PINGPONG
+#define SG_ATTN_PINGPONG 1
+#endif
+constexpr bool kPingPong = SG_ATTN_PINGPONG != 0;  // staggered exp phases of the two softmax warpgroups
+#ifndef SG_ATTN_HANDOFF
+#define SG_ATTN_HANDOFF 0
+#endif
+constexpr int kHandoff = SG_ATTN_HANDOFF;  // the other warpgroup may start its exps once chunk kHandoff (of 4) is issued
 
 struct AttnKParams {
   CUtensorMap q_map, k_map, v_map;
@@ -311,23 +319,34 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
 
     float m_used = 0.f, l_run = 0.f;
     if constexpr (QT == 2) {
-      if (tq == 1) named_bar_arrive(1, 256);  // warpgroup 0 owns the exp unit first
+      if (kPingPong && tq == 1) named_bar_arrive(1, 256);  // warpgroup 0 owns the exp unit first
     }
     // one KV tile of the online softmax; kMasked is only instantiated for the LAST tile (ragged nk), so the
     // 128-element mask (ISETP + SEL per element once if-converted) stays out of the steady-state loop
+    // S row of the current tile.  kSepP streams it: as soon as the exps of a 32-column chunk of tile j are done, the
+    // same registers receive that chunk of S(j+1) (tcgen05.ld is asynchronous), so the TMEM read and the wait for
+    // Q K_{j+1}^T leave the per-tile critical path.
+    uint32_t sv[4][32];
+    if constexpr (Cfg::kSepP) {
+      mbar_wait(&s_full[tq], 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_base + lane_base + tq * 128 + c * 32, sv[c]);
+    }
     auto softmax_tile = [&](const int j, auto masked_tag) {
       constexpr bool kMasked = decltype(masked_tag)::value;
       const int sb = (QT == 2) ? tq : (j & 1);                         // S / P buffer
-      const uint32_t s_par = (QT == 2) ? (j & 1) : ((j >> 1) & 1);
+      [[maybe_unused]] const uint32_t s_par = (QT == 2) ? (j & 1) : ((j >> 1) & 1);
       uint64_t* od = &o_done[(QT == 2) ? tq : 0];
-      SG_TS(0);
-      mbar_wait(&s_full[sb], s_par);
-      tc_fence_after();
-      SG_TS(1);
       const uint32_t s_tmem = tmem_base + lane_base + sb * 128;
-      uint32_t sv[4][32];
+      SG_TS(0);
+      if constexpr (!Cfg::kSepP) {
+        mbar_wait(&s_full[sb], s_par);
+        tc_fence_after();
+        SG_TS(1);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
+        for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
+      }
       tmem_ld_wait();
       if constexpr (Cfg::kSepP) {
         // S_t(j) is in registers: the tensor core may overwrite it with Q_t K_{j+1}^T
@@ -384,7 +403,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
           }
         }
       };
-      if constexpr (QT == 2) wait_and_rescale();  // already satisfied: QK_{j} was issued after PV_{j-1}
+      if constexpr (QT == 2 && !Cfg::kSepP) wait_and_rescale();  // already satisfied: QK_{j} was issued after PV_{j-1}
       float sum4[4] = {0.f, 0.f, 0.f, 0.f};
       const float nm = -m_used;
       if constexpr (QT == 2) {
@@ -393,7 +412,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
         // behind the MMA chain); with the exp phase made exclusive, one group's TMEM load / row max / P store
         // / wait for the tensor core overlaps the other group's exps.  Barrier 1 + t admits warpgroup t.
         SG_TS(3);
-        named_bar_sync(1 + tq, 256);
+        if (kPingPong) named_bar_sync(1 + tq, 256);
         SG_TS(4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -405,11 +424,26 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
             sum4[(i >> 1) & 3] += e0 + e1;
             pk[i >> 1] = pack_bf16x2(e0, e1);
           }
+          if constexpr (Cfg::kSepP) {
+            // PV_{j-1} must have retired before P_j overwrites P_{j-1}; its ~500 clk hide behind the row max and
+            // the first chunk of exps
+            if (c == 0) wait_and_rescale();
+          }
           tmem_st16((Cfg::kSepP ? (tmem_base + lane_base + Cfg::kColP + tq * 64) : s_tmem) + c * 16, pk);
+          // admit the other warpgroup (its tile j if we are group 0, tile j+1 if we are group 1)
+          if (kPingPong && c == kHandoff && !(tq == 1 && j == T - 1)) named_bar_arrive(2 - tq, 256);
+          if constexpr (Cfg::kSepP) {
+            if (j + 1 < T) {
+              if (c == 0) {
+                mbar_wait(&s_full[tq], (j + 1) & 1);
+                tc_fence_after();
+                SG_TS(1);
+              }
+              tmem_ld32(s_tmem + c * 32, sv[c]);  // S(j+1), chunk c -> the registers chunk c of S(j) just left
+            }
+          }
         }
-        // hand the exp unit to the other warpgroup (its tile j if we are group 0, tile j+1 if we are group 1)
         SG_TS(5);
-        if (!(tq == 1 && j == T - 1)) named_bar_arrive(2 - tq, 256);
       } else {
         uint32_t pk[2][32];
 #pragma unroll

@@ -109,6 +109,7 @@ void test_ubench_cp();
 void test_ubench_mma_multi();
 void test_ubench_mma_var();
 void test_ubench_tma();
+void test_ubench_softmax_mix();
 void test_timeline();
 void test_gemm_timeline();
 void test_extra() {
@@ -118,6 +119,7 @@ void test_extra() {
   test_ubench_mma_multi();
   test_ubench_mma_var();
   test_ubench_tma();
+  test_ubench_softmax_mix();
   test_timeline();
   test_gemm_timeline();
   run_attn_case("attn d40 self 2x8 nq=nk=256", 40, 8, 2, 2, 256, 256, 1.f, false, {});
@@ -217,7 +219,8 @@ void test_timeline() {
 }
 void test_gemm_timeline() {
   if (!want("gtimeline")) return;
-  const int M = 98304, N = 2560, K = 320;
+  const int M = getenv("GT_M") ? atoi(getenv("GT_M")) : 98304, N = getenv("GT_N") ? atoi(getenv("GT_N")) : 2560,
+            K = getenv("GT_K") ? atoi(getenv("GT_K")) : 320;
   HostBf A, B, O;
   A.init(1ll * M * K, 1.f);
   B.init(1ll * N * K, 0.05f);
@@ -543,6 +546,79 @@ void test_ubench_tma() {
     }
   cudaFree(cyc);
   cudaFree(buf);
+}
+
+// softmax inner loop candidates: exp2 (+row-sum FADD) alone / + cvt.rn.bf16x2.f32 per pair / + integer
+// round-half-up pack (2 IADD + PRMT per pair) / + exp2 replaced by a degree-3 polynomial on the FMA pipe for 1 in 4
+template <int V>
+__global__ void ubench_softmax_mix(int iters, long long* cycles, float* sink) {
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = -0.001f * (threadIdx.x + i);
+  float sum = 0.f;
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    float e[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float a = fmaf(x[i], 1.0009f, -0.25f);
+      if (V == 3 && (i & 3) == 3) {
+        // 2^a for a <= 0: Cody-Waite split + cubic on the fractional part (FMA pipe only)
+        const float fl = floorf(a);
+        const float f = a - fl;
+        float pz = fmaf(f, 0.0555054f, 0.2402265f);
+        pz = fmaf(pz, f, 0.6931472f);
+        pz = fmaf(pz, f, 1.0f);
+        e[i] = __uint_as_float(__float_as_uint(pz) + (static_cast<int>(fl) << 23));
+      } else {
+        e[i] = sg::fast_exp2(a);
+      }
+      sum += e[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      if (V == 1) acc ^= sg::pack_bf16x2(e[i], e[i + 1]);
+      if (V == 2 || V == 3) {
+        const uint32_t lo = __float_as_uint(e[i]) + 0x8000u, hi = __float_as_uint(e[i + 1]) + 0x8000u;
+        acc ^= __byte_perm(lo, hi, 0x7632);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = e[i] - 1.5f;
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  float a = sum + __uint_as_float(acc & 0x3fffffffu);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a += x[i];
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = a;
+}
+template <int V>
+static void run_softmax_mix(long long* cyc, float* sink, const char* what) {
+  for (int warps : {4, 8}) {
+    const int iters = 4000;
+    ubench_softmax_mix<V><<<148, warps * 32>>>(iters, cyc, sink);
+    CK(cudaDeviceSynchronize());
+    long long h;
+    CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    printf("[ubench] softmax mix %-46s %d warps/SM: %.2f elements/clk/SM\n", what, warps,
+           static_cast<double>(iters) * 16 * warps * 32 / h);
+  }
+}
+void test_ubench_softmax_mix() {
+  if (!want("ubench4")) return;
+  long long* cyc;
+  float* sink;
+  CK(cudaMalloc(&cyc, 8 * 1024));
+  CK(cudaMalloc(&sink, 4 * 1024 * 1024));
+  run_softmax_mix<0>(cyc, sink, "FFMA + ex2 + FADD");
+  run_softmax_mix<1>(cyc, sink, "... + cvt.rn.bf16x2.f32 per pair");
+  run_softmax_mix<2>(cyc, sink, "... + integer pack (2 IADD + PRMT) per pair");
+  run_softmax_mix<3>(cyc, sink, "... integer pack, 1 in 4 exps as FMA polynomial");
+  cudaFree(cyc);
+  cudaFree(sink);
 }
 
 // TS-mode GEMM feasibility: per k-block 4 x tcgen05.cp (smem A [128 x 16] -> TMEM, 128x256b) + 4 x TS MMA
