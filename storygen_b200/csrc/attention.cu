@@ -30,7 +30,12 @@ constexpr bool kPingPong = SG_ATTN_PINGPONG != 0;  // staggered exp phases of th
 #ifndef SG_ATTN_HANDOFF
 #define SG_ATTN_HANDOFF 0
 #endif
-constexpr int kHandoff = SG_ATTN_HANDOFF;  // the other warpgroup may start its exps once chunk kHandoff (of 4) is issued
+constexpr int kHandoff = SG_ATTN_HANDOFF;
+#ifndef SG_ATTN_POLY_EVERY
+#define SG_ATTN_POLY_EVERY 8
+#endif
+constexpr int kPolyPairs = SG_ATTN_POLY_EVERY > 0 ? SG_ATTN_POLY_EVERY / 2 : 1;
+constexpr int kPolyEvery = SG_ATTN_POLY_EVERY;  // 0 = all exps on MUFU; 4 = 1 in 4 on the FMA pipe; 2 = 1 in 2  // the other warpgroup may start its exps once chunk kHandoff (of 4) is issued
 
 struct AttnKParams {
   CUtensorMap q_map, k_map, v_map;
@@ -419,8 +424,11 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float e0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, nm));
-            const float e1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, nm));
+            const float x0 = fmaf(__uint_as_float(sv[c][i]), p.scale_log2, nm);
+            const float x1 = fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, nm);
+            // the MUFU pipe (16 exp2 / clk / SM) bounds this loop: every kPolyEvery-th exp runs on the FMA pipe instead
+            const float e0 = fast_exp2(x0);
+            const float e1 = (kPolyEvery > 0 && ((i >> 1) % kPolyPairs) == 0) ? exp2_fma(x1) : fast_exp2(x1);
             sum4[(i >> 1) & 3] += e0 + e1;
             pk[i >> 1] = pack_bf16x2(e0, e1);
           }

@@ -263,69 +263,77 @@ __global__ void timestep_features_kernel(const float* __restrict__ t, int n, int
   out[r * dim + half + i] = sinf(arg);
 }
 
-// out[r][m] = act_out( sum_k W[m][k] * act_in(x[r][k]) + b[m] ).  Block = 8 warps = 32 output features; every warp
-// keeps 4 weight rows in registers (k <= 1280) and the block streams the n activation rows through shared memory in
-// chunks of 8 rows (act_in applied once while staging), so x is read from L2 once per 32 features.
-// Element mapping inside a row: float4 index q = i*64 + h*32 + lane (i < 5, h < 2) -> conflict-free LDS.128.
-constexpr int kSlF = 4;      // features per warp
-constexpr int kSlWarps = 8;  // warps per block
-constexpr int kSlRows = 8;   // activation rows staged per chunk
-__global__ void small_linear_kernel(const float* __restrict__ x, int n, int k, const bf16* __restrict__ w,
-                                    const float* __restrict__ b, int m, int silu_in, int silu_out,
-                                    float* __restrict__ out) {
-  extern __shared__ float xs[];  // [kSlRows][k]
+// out[r][m] = act_out( sum_k W[m][k] * act_in(x[r][k]) + b[m] ) for a handful of rows (image lanes).
+// One block per SM: all n activation rows are staged ONCE into shared memory (fp32, act_in applied), then every warp
+// walks output features two at a time: the two weight rows are streamed from HBM/L2 exactly once (bf16, 8-byte
+// coalesced loads kept in registers), each x value read from smem feeds both features, and the per-lane partial
+// sums of up to kSlMaxRows rows are folded with shuffles.  Element mapping inside a row: float4 index
+// q = i * 32 + lane (i < 10) -> conflict-free LDS.128.  Rows beyond kSlMaxRows are processed in further passes.
+constexpr int kSlMaxRows = 24;  // rows per pass (accumulators: 2 features x 24 rows = 48 registers)
+constexpr int kSlWarps = 16;
+__global__ void __launch_bounds__(kSlWarps * 32, 1)
+    small_linear_kernel(const float* __restrict__ x, int n, int k, const bf16* __restrict__ w,
+                        const float* __restrict__ b, int m, int silu_in, int silu_out, float* __restrict__ out) {
+  extern __shared__ float xs[];  // [min(n, kSlMaxRows)][k]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row0 = (blockIdx.x * kSlWarps + warp) * kSlF;
   const int Q = k / 4;  // float4 per row
-  float wf[kSlF][5][2][4];
-#pragma unroll
-  for (int f = 0; f < kSlF; ++f)
-#pragma unroll
-    for (int i = 0; i < 5; ++i)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int q = i * 64 + h * 32 + lane;
-        float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
-        if (row0 + f < m && q < Q) {
-          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(w + static_cast<long long>(row0 + f) * k + q * 4));
-          lo = unpack_bf16x2(raw.x);
-          hi = unpack_bf16x2(raw.y);
-        }
-        wf[f][i][h][0] = lo.x; wf[f][i][h][1] = lo.y; wf[f][i][h][2] = hi.x; wf[f][i][h][3] = hi.y;
-      }
-  for (int r0 = 0; r0 < n; r0 += kSlRows) {
-    const int rows = (n - r0) < kSlRows ? (n - r0) : kSlRows;
-    __syncthreads();  // previous chunk fully consumed
+  for (int r0 = 0; r0 < n; r0 += kSlMaxRows) {
+    const int rows = (n - r0) < kSlMaxRows ? (n - r0) : kSlMaxRows;
+    __syncthreads();  // previous pass fully consumed
     for (int idx = threadIdx.x; idx < rows * Q; idx += blockDim.x) {
       float4 v = __ldg(reinterpret_cast<const float4*>(x + static_cast<long long>(r0) * k) + idx);
       if (silu_in) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
       reinterpret_cast<float4*>(xs)[idx] = v;
     }
     __syncthreads();
-    if (row0 < m) {
-      for (int r = 0; r < rows; ++r) {
-        float acc[kSlF] = {0.f, 0.f, 0.f, 0.f};
-        const float4* xr = reinterpret_cast<const float4*>(xs + r * k);
+    // feature pairs are dealt round-robin to all warps of all blocks
+    for (int f0 = 2 * (blockIdx.x * kSlWarps + warp); f0 < m; f0 += 2 * gridDim.x * kSlWarps) {
+      const bool two = (f0 + 1 < m);
+      float acc0[kSlMaxRows], acc1[kSlMaxRows];
 #pragma unroll
-        for (int i = 0; i < 5; ++i)
+      for (int r = 0; r < kSlMaxRows; ++r) acc0[r] = acc1[r] = 0.f;
+      uint2 w0[10], w1[10];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int q = i * 64 + h * 32 + lane;
-            if (q < Q) {
-              const float4 xv = xr[q];
+      for (int i = 0; i < 10; ++i) {
+        const int q = i * 32 + lane;
+        w0[i] = (q < Q) ? __ldg(reinterpret_cast<const uint2*>(w + static_cast<long long>(f0) * k) + q) : make_uint2(0, 0);
+        w1[i] = (two && q < Q) ? __ldg(reinterpret_cast<const uint2*>(w + static_cast<long long>(f0 + 1) * k) + q)
+                               : make_uint2(0, 0);
+      }
 #pragma unroll
-              for (int f = 0; f < kSlF; ++f)
-                acc[f] = fmaf(wf[f][i][h][0], xv.x, fmaf(wf[f][i][h][1], xv.y, fmaf(wf[f][i][h][2], xv.z, fmaf(wf[f][i][h][3], xv.w, acc[f]))));
+      for (int i = 0; i < 10; ++i) {
+        const int q = i * 32 + lane;
+        if (q < Q) {
+          const float2 a0 = unpack_bf16x2(w0[i].x), a1 = unpack_bf16x2(w0[i].y);
+          const float2 c0 = unpack_bf16x2(w1[i].x), c1 = unpack_bf16x2(w1[i].y);
+#pragma unroll
+          for (int r = 0; r < kSlMaxRows; ++r) {
+            if (r < rows) {
+              const float4 xv = reinterpret_cast<const float4*>(xs + r * k)[q];
+              acc0[r] = fmaf(a0.x, xv.x, fmaf(a0.y, xv.y, fmaf(a1.x, xv.z, fmaf(a1.y, xv.w, acc0[r]))));
+              acc1[r] = fmaf(c0.x, xv.x, fmaf(c0.y, xv.y, fmaf(c1.x, xv.z, fmaf(c1.y, xv.w, acc1[r]))));
             }
           }
+        }
+      }
+      const float b0 = b ? b[f0] : 0.f, b1 = (b && two) ? b[f0 + 1] : 0.f;
 #pragma unroll
-        for (int f = 0; f < kSlF; ++f) {
-          float a = acc[f];
+      for (int r = 0; r < kSlMaxRows; ++r) {
+        if (r < rows) {
+          float s0 = acc0[r], s1 = acc1[r];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-          if (lane == 0 && row0 + f < m) {
-            const float y = a + (b ? b[row0 + f] : 0.f);
-            out[static_cast<long long>(r0 + r) * m + row0 + f] = silu_out ? silu_f(y) : y;
+          for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          }
+          if (lane == 0) {
+            float* dst = out + static_cast<long long>(r0 + r) * m + f0;
+            const float y0 = s0 + b0;
+            dst[0] = silu_out ? silu_f(y0) : y0;
+            if (two) {
+              const float y1 = s1 + b1;
+              dst[1] = silu_out ? silu_f(y1) : y1;
+            }
           }
         }
       }
@@ -476,9 +484,18 @@ extern "C" int sg_small_linear(const float* x, int32_t n, int32_t k, const void*
                                int32_t silu_in, int32_t silu_out, float* out, void* stream) {
   if (!x || !w || !out) return SG_ERR_ARG;
   if (k % 8 || k > 1280) return SG_ERR_SHAPE;
-  const int feats_per_block = kSlWarps * kSlF;
-  const size_t smem = static_cast<size_t>(kSlRows) * k * sizeof(float);
-  small_linear_kernel<<<(m + feats_per_block - 1) / feats_per_block, kSlWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+  const int rows = n < kSlMaxRows ? n : kSlMaxRows;
+  const size_t smem = static_cast<size_t>(rows) * k * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSlMaxRows * 1280 * static_cast<int>(sizeof(float)));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  int blocks = (m + 2 * kSlWarps - 1) / (2 * kSlWarps);
+  if (blocks > num_sms()) blocks = num_sms();
+  small_linear_kernel<<<blocks, kSlWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       x, n, k, static_cast<const bf16*>(w), b, m, silu_in, silu_out, out);
   SG_LAUNCH_END();
 }

@@ -166,6 +166,11 @@ def test_time_embedding_chain():
     w, b = rnd(temb, dim, scale=dim ** -0.5, seed=1), rnd(temb, seed=2, dtype=torch.float32)
     y = ops.small_linear(f, w, b, torch.empty(n, temb, device=DEV), silu_in=True, silu_out=True)
     close(y, F.silu(F.silu(f) @ w.float().T + b), rel=1e-3, abs_=1e-3)
+    # more rows than one pass holds (24), an odd feature count, k = 1280, no bias / no activations
+    x2 = rnd(29, 1280, seed=3, dtype=torch.float32)
+    w2 = rnd(331, 1280, scale=1280 ** -0.5, seed=4)
+    y2 = ops.small_linear(x2, w2, None, torch.empty(29, 331, device=DEV))
+    close(y2, x2 @ w2.float().T, rel=1e-3, abs_=1e-3)
 
 
 def test_upsample_conv_in_out_and_scheduler_kernels():
