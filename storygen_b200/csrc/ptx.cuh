@@ -51,6 +51,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+#pragma unroll 1  // unrolled 64x by default: ~200 instructions of spin code per wait site
   for (uint32_t it = 0; it < (1u << 26); ++it) {
     asm volatile(
         "{\n"
