@@ -1,0 +1,16 @@
+"""One d=40 self-attention launch (12 lanes) for `ncu --set full` captures.  Usage: python scripts/attn_one.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from storygen_b200 import ops
+from storygen_b200.ops import BF16
+
+lanes, heads, d, nq, nk = 12, 8, 40, 4096, 4096
+c = heads * d
+q = torch.randn(lanes, nq, c, device="cuda").to(BF16)
+k = torch.randn(lanes, nk, c, device="cuda").to(BF16)
+v = torch.randn(lanes, nk, c, device="cuda").to(BF16)
+o = torch.empty(lanes, nq, c, device="cuda", dtype=BF16)
+for _ in range(3):
+    ops.attention(q, k, v, o, lanes, heads, d, nq, nk, (nq * c, c), (nk * c, c), (nk * c, c))
+torch.cuda.synchronize()

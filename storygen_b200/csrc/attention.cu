@@ -409,8 +409,8 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
         }
       };
       if constexpr (QT == 2 && !Cfg::kSepP) wait_and_rescale();  // already satisfied: QK_{j} was issued after PV_{j-1}
-      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
-      const float nm = -m_used;
+      float2 sum2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float2 nm2 = make_float2(-m_used, -m_used), sc2 = make_float2(p.scale_log2, p.scale_log2);
       if constexpr (QT == 2) {
         // Warpgroup ping-pong on the MUFU pipe: the two softmax warpgroups share each sub-partition's
         // 4-lane/clk exp unit.  Left alone they fall into lockstep (both in the exp phase, then both idle
@@ -424,12 +424,12 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float x0 = fmaf(__uint_as_float(sv[c][i]), p.scale_log2, nm);
-            const float x1 = fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, nm);
+            // packed FFMA2 / FADD2: one issue slot scales two scores / accumulates two exps
+            const float2 x = ffma2(make_float2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sc2, nm2);
             // the MUFU pipe (16 exp2 / clk / SM) bounds this loop: every kPolyEvery-th exp runs on the FMA pipe instead
-            const float e0 = fast_exp2(x0);
-            const float e1 = (kPolyEvery > 0 && ((i >> 1) % kPolyPairs) == 0) ? exp2_fma(x1) : fast_exp2(x1);
-            sum4[(i >> 1) & 3] += e0 + e1;
+            const float e0 = fast_exp2(x.x);
+            const float e1 = (kPolyEvery > 0 && ((i >> 1) % kPolyPairs) == 0) ? exp2_fma(x.y) : fast_exp2(x.y);
+            sum2[(i >> 1) & 3] = fadd2(sum2[(i >> 1) & 3], make_float2(e0, e1));
             pk[i >> 1] = pack_bf16x2(e0, e1);
           }
           if constexpr (Cfg::kSepP) {
@@ -458,16 +458,18 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
         for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float e0 = fast_exp2(fmaf(__uint_as_float(sv[c][i]), p.scale_log2, nm));
-            const float e1 = fast_exp2(fmaf(__uint_as_float(sv[c][i + 1]), p.scale_log2, nm));
-            sum4[(i >> 1) & 3] += e0 + e1;
+            const float2 x = ffma2(make_float2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sc2, nm2);
+            const float e0 = fast_exp2(x.x);
+            const float e1 = fast_exp2(x.y);
+            sum2[(i >> 1) & 3] = fadd2(sum2[(i >> 1) & 3], make_float2(e0, e1));
             pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
           }
         wait_and_rescale();  // late: the exps above overlap PV_{j-1}
         tmem_st32(s_tmem, pk[0]);
         tmem_st32(s_tmem + 32, pk[1]);
       }
-      l_run = l_run * alpha + ((sum4[0] + sum4[1]) + (sum4[2] + sum4[3]));
+      const float2 s01 = fadd2(sum2[0], sum2[1]), s23 = fadd2(sum2[2], sum2[3]);
+      l_run = l_run * alpha + ((s01.x + s01.y) + (s23.x + s23.y));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

@@ -365,6 +365,34 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): two IEEE fp32 results per lane for one issue slot.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "mov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n"
+      ".reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "add.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 // 2^x on the FMA pipe (no MUFU): round-to-nearest range reduction with the 1.5 * 2^23 trick, cubic minimax on
 // [-0.5, 0.5] (relative error 7.5e-5, far below the bf16 rounding of P), exponent inserted with an integer add.
 // Inputs are clamped to >= -125 so the result stays a normal number (masked scores -> 2^-125).
