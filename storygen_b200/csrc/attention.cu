@@ -174,7 +174,13 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
     // ===================== MMA issuer(s) (whole warp; one elected lane issues) =====================
     {
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
+      // B (= V) is MN-major; only the head's own channels are multiplied: atom a covers min(64, D - 64a) channels
+      // rounded up to the UMMA N granularity of 16 (d = 40 -> N = 48 instead of 64: fewer wasted tensor FLOPs)
+      auto idesc_pv_of = [](int a) {
+        const int rem = D - 64 * a;
+        const int n = rem >= 64 ? 64 : ((rem + 15) & ~15);
+        return make_idesc_bf16(128, static_cast<uint32_t>(n), 0, 1);
+      };
       auto qk = [&](uint32_t q_addr, uint32_t k_addr, uint32_t s_col) {
 #pragma unroll
         for (int ks = 0; ks < Cfg::KQ; ++ks) {
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
           for (int ks = 0; ks < 8; ++ks) {
             // V tile rows = keys (128 B pitch); 16 keys per k-step = 2048 B
             umma_ts_w(tmem_base + o_col + 64 * a, tmem_base + p_col + ks * 8,
-                    make_smem_desc(v_addr + a * kAtomBytes + ks * 2048, kAtomBytes, 1024, kLayoutSW128), idesc_pv,
+                    make_smem_desc(v_addr + a * kAtomBytes + ks * 2048, kAtomBytes, 1024, kLayoutSW128), idesc_pv_of(a),
                     !(first && ks == 0));
           }
         }
