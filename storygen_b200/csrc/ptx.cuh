@@ -51,8 +51,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+  long long t0 = 0;
 #pragma unroll 1  // unrolled 64x by default: ~200 instructions of spin code per wait site
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  for (uint32_t it = 0;; ++it) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -63,6 +64,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
+    // time-based bound (~2 s of SM clocks), checked every 256 polls: a lost arrive becomes a launch error quickly
+    if ((it & 255u) == 255u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) break;
+    }
   }
   __trap();
 }
