@@ -201,14 +201,15 @@ def kernel_rooflines(torch, peaks, lanes):
     t = timeit(lambda i: ops.gemm([Src.nhwc(xs[i])], taps3x3(0, c), (w, h, lanes), wt, ys[i], bias=b), 4)
     flops = 2.0 * lanes * h * w * c * 9 * c
     # traffic = dram__bytes_read.sum + dram__bytes_write.sum of this kernel inside a step at 24 lanes (ncu --set full,
-    # profiles/r01_ncu_full_prof_conv_r01b.csv): 64.9 + 26.0 MB < 127.7 MB algorithmic (input still L2-resident)
-    traffic = 90911232 if lanes == 24 else None
+    # profiles/r01_final_ncu_full_conv.csv): 64.9 MB read + 17.5 MB written < 127.7 MB algorithmic (part of the output is still in L2 at kernel end)
+    traffic = 82338816 if lanes == 24 else None
     out["conv3x3_320_L0"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                              "frac": flops / t / 1e12 / peaks["tf_burst"], "traffic": traffic,
                              "algorithmic_bytes": 2 * lanes * h * w * c * 2 + 9 * c * c * 2,
-                             "note": "tcgen05.mma M128 N160 K16 (SS) costs 167 clk per instruction for 80 clk of math "
-                                     "(profiles/r01_ubench_mma_cost.log): a 1-CTA kernel of this tile shape tops out at ~48-52 % of "
-                                     "the tensor peak; cuBLAS' 1676 TFLOP/s 'measured peak' uses 256-wide 2-CTA tiles",
+                             "note": "N = 320 runs as two 160-wide tiles: per 64-deep k-block a CTA pulls A 16 KB + B 20 KB into shared "
+                                     "memory for 4 x 80 clk of tcgen05 math = 115 B/clk/SM demanded vs ~80-100 B/clk/SM that TMA delivers "
+                                     "from L2 with all SMs active (profiles/r01_ubench_tma_ingest.log): operand-ingest bound, not "
+                                     "issue bound (issue streams run at the math rate: profiles/r01_ubench_issue_stream.log)",
                              "flops_per_launch": flops, "ms_per_launch": t * 1e3, "lanes": lanes}
     # (2) L0 image cross-attention core: Nq = 4096, Nk = 3 * 4096, 8 heads x d40
     hd, heads, nq, nk = 40, 8, 4096, 3 * 4096
@@ -222,8 +223,9 @@ def kernel_rooflines(torch, peaks, lanes):
     out["attn3_core_L0"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                             "frac": flops / t / 1e12 / peaks["tf_burst"], "traffic": None, "flops_per_launch": flops,
                             "ms_per_launch": t * 1e3, "lanes": ql,
-                            "note": "d=40: one 128x128 tile = 3 QK^T + 8 PV tcgen05.mma at ~160/~132 clk each = 1536 clk of tensor-pipe "
-                                    "issue time (math: 384 clk) vs 1024 clk of MUFU exp time: tensor-ISSUE bound, measured ~1700 clk/tile"}
+                            "note": "d=40: a 128x128 tile needs 16384 exp2 = 1024 clk of MUFU (16/clk/SM; 896 clk with 1 in 8 exps "
+                                    "on the FMA pipe) but only ~580 clk of tensor pipe (3 QK^T + 8 PV MMAs): exp-unit bound; ncu: "
+                                    "XU pipe 68 %, measured ~1450 SM-clk per tile"}
     del xs, ys, q, k, v, o
     torch.cuda.empty_cache()
     return out

@@ -227,9 +227,17 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
     if (rc != 0) return rc;
   }
 
-  // tile width: per tcgen05.mma the cost is ~128 + N/4 clk (profiles/r01_ubench_mma_cost.log), so 256-wide tiles with a
-  // ragged last tile beat 160-wide ones from N = 512 on (N = 640: 2 x 194 + 160 vs 4 x 167 clk per k-step)
-  const int bn_tile = (a->N % 256 == 0 || a->N >= 512) ? 256 : ((a->N % 160 == 0) ? 160 : ((a->N % 128 == 0) ? 128 : 64));
+  // tile width: the main loop is bound by the bytes an SM must pull into shared memory per MMA (A 16 KB + B 128 B x BN
+  // per k-block, ~80-100 B/clk/SM achievable: profiles/r01_ubench_tma_ingest.log), so wide tiles win: 256 with a
+  // ragged last tile from N = 512 on.  Small problems (deep UNet levels: M = 768 / 1536 rows) are the exception: when
+  // the tile count would leave more than half of the SMs idle, halve the tile width until the grid fills them.
+  int bn_tile = (a->N % 256 == 0 || a->N >= 512) ? 256 : ((a->N % 160 == 0) ? 160 : ((a->N % 128 == 0) ? 128 : 64));
+  {
+    const long long m_tiles = static_cast<long long>((a->out_w + a->bw - 1) / a->bw) * ((a->out_h + a->bh - 1) / a->bh) *
+                              ((a->out_n + a->bn - 1) / a->bn);
+    while (bn_tile > 64 && bn_tile % 128 == 0 && m_tiles * ((a->N + bn_tile - 1) / bn_tile) * 2 <= num_sms())
+      bn_tile /= 2;
+  }
   {
     uint64_t dims[2] = {static_cast<uint64_t>(a->Ktot), static_cast<uint64_t>(a->N)};
     uint64_t strides[1] = {static_cast<uint64_t>(a->Ktot) * 2};
