@@ -35,6 +35,38 @@ def test_linear_bias_residual(m, k, n):
     close(out, x.float() @ w.float().T + b + 2.0 * r.float())
 
 
+@pytest.mark.parametrize("m,k,n,why", [
+    (3840, 320, 640, "90 tiles: 256-wide tiles with a ragged 128-column last tile"),
+    (256, 640, 1280, "10 tiles: tile width halved twice (64) so that the grid fills the SMs"),
+    (1536, 1280, 1280, "60 tiles: tile width halved once (128), the deep-level conv shape class"),
+    (98304 // 8, 320, 960, "fused QKV: N = 960 as 256+256+256+192"),
+])
+def test_linear_tile_width_selection(m, k, n, why):
+    """sg_gemm picks the N tile width from the problem size (gemm.cu); every choice must give the same numbers."""
+    x, w = rnd(m, k, seed=5), rnd(n, k, scale=k ** -0.5, seed=6)
+    b = rnd(n, seed=7, dtype=torch.float32)
+    out = torch.empty(m, n, dtype=BF16, device=DEV)
+    ops.linear(x, w, out, bias=b)
+    close(out, x.float() @ w.float().T + b)
+
+
+def test_geglu_gelu_is_the_exact_erf_form():
+    """The epilogue's one-MUFU GELU (2^(z P7(z)) = erfc(z)) against torch's erf GELU over a wide gate range, including
+    the negative tail where a tanh approximation would be off by several bf16 ulps."""
+    m, c = 256, 64
+    # value weights = identity rows (value = x), gate weights = scaled identity (gate sweeps [-9, 9])
+    x = torch.linspace(-1.5, 1.5, m * c).reshape(m, c).to(BF16).to(DEV)
+    wv, wg = torch.eye(c), 6.0 * torch.eye(c)
+    w = torch.cat([wv, wg], 0).to(BF16).to(DEV)
+    wi = torch.stack([w[:c].reshape(-1, 16, c), w[c:].reshape(-1, 16, c)], 1).reshape(2 * c, c).contiguous()
+    out = torch.empty(m, c, dtype=BF16, device=DEV)
+    ops.linear(x, wi, out, mode=_lib.SG_EPI_GEGLU)
+    xf = x.float()
+    ref = xf * F.gelu(6.0 * xf)
+    err = (out.float() - ref).abs()
+    assert (err <= 2.0 ** -8 * ref.abs() + 1e-6).all(), f"max err {err.max().item():.3g}"  # one bf16 rounding
+
+
 def test_linear_geglu():
     m, c = 512, 320
     x, w, b = rnd(m, c, seed=1), rnd(8 * c, c, scale=c ** -0.5, seed=2), rnd(8 * c, seed=3, dtype=torch.float32)

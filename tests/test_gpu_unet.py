@@ -18,6 +18,7 @@ from oracle.weights import load_seeded
 from storygen_b200 import DDIMScheduler, StableDiffusionPipeline, UNet2DConditionModel, _lib
 
 pytestmark = pytest.mark.gpu
+DEV = "cuda"
 REL = 0.10
 
 
@@ -89,6 +90,26 @@ def test_unet_batch_invariance_and_timestep_forms(tiny):
     assert torch.equal(full[1:2], one), "lanes must not influence each other (CFG lane de-duplication relies on it)"
     zero_d = mod(x[1:2].cuda(), torch.tensor(int(t[1])), txt[1:2].cuda(), return_dict=False)[0]
     assert torch.equal(zero_d, one)
+
+
+def test_text_kv_cache_is_bit_identical(tiny):
+    """The pipeline projects the attn2 text K/V of all layers once per prompt (UNetEngine.project_text) and feeds
+    them to every step; the result must equal the self-contained forward bit for bit."""
+    _, unet = tiny
+    eng = unet.engine()
+    g = torch.Generator("cpu").manual_seed(11)
+    n, L, D = 3, 77, unet.config.cross_attention_dim
+    sample = torch.randn(n, 4, 32, 32, generator=g).to(DEV)
+    text = torch.randn(n, L, D, generator=g).to(DEV)
+    t = torch.tensor([981.0, 500.0, 1.0], device=DEV)
+    out_a, taps_a = eng.forward(sample, t, text)
+    kv = eng.project_text(text)
+    assert tuple(kv.shape) == (n * L, eng.n_kv2)
+    out_b, taps_b = eng.forward(sample, t, text, text_kv=kv)
+    assert torch.equal(out_a, out_b)
+    assert all(torch.equal(taps_a[k], taps_b[k]) for k in taps_a)
+    with pytest.raises(ValueError):
+        eng.forward(sample, t, text, text_kv=kv[:-1])
 
 
 def test_full_size_sd15_unet_vs_oracle():
