@@ -1,21 +1,24 @@
-// Fused attention core for sm_100a: o = softmax(scale * Q K^T) V per (image lane, head), one CTA per
-// 128-query tile, S / P / O resident in TMEM, K/V streamed by TMA.
+// Fused attention core for sm_100a: o = softmax(scale * Q K^T) V per (image lane, head); S / P / O resident in
+// TMEM, K/V streamed by TMA through a ring of 128-key tiles.
 //
-//   warp 0     : TMA loader   Q tile once; K/V tiles of 128 keys through a ring of smem slots in the
-//                             exact order the tensor core consumes them (K0 K1 V0 K2 V1 ...)
-//   warp 1     : MMA issuer   S[b] = Q K_j^T            (tcgen05.mma SS, M=128 N=128, K = head_dim)
-//                             O   += P_j V_j            (tcgen05.mma TS: P read from TMEM, V MN-major)
-//                             QK^T of tile j+1 is issued before waiting for the softmax of tile j
-//   warps 2..5 : softmax      one thread per query row (= TMEM lane): S row -> registers, running max
-//                             with lazy rescale of the O row (only when the max grew by > 2^8),
-//                             exp2, row sum, P (bf16) written back over S, final O / l -> global.
-//   (QT == 2)  : warps 6..9 are a second softmax warpgroup for a second 128-query tile: the two tiles
-//                ping-pong on the tensor core and share every K/V tile (head dims <= 128).
+// QT == 2 (Nq > 128, head dim <= 128): two 128-query tiles per CTA, 12 warps
+//   warp 0      : TMA loader   both Q tiles once; K0 V0 K1 V1 ... through the ring (shared by both query tiles)
+//   warp 1      : Q K^T issuer S_t = Q_t K_j^T (tcgen05.mma SS, M=128 N=128) as soon as K_j has landed and the
+//                              softmax warps have READ S_t(j-1) [head dims <= 64: P has its own TMEM columns]
+//   warp 2      : P V issuer   O_t += P_t V_j (tcgen05.mma TS: P read from TMEM, V MN-major, N = the head's channels)
+//                              (head dims > 64: warp 1 issues both, in order)
+//   warp 3      : idle         (warps 0..3 shrink to 64 registers, the softmax warps grow to 216: setmaxnreg)
+//   warps 4..11 : softmax      one warpgroup per query tile, one thread per query row (= TMEM lane): S row in
+//                              registers (streamed: chunk c of S(j+1) replaces chunk c of S(j)), running max with
+//                              lazy rescale of the O row (only when the max grew by > 2^8), exp2 (MUFU, 1 in 8 on
+//                              the FMA pipe), row sum, P (bf16) -> TMEM, final O / l -> global
+//   All issue loops are warp-uniform with one elected lane issuing (ptx.cuh: *_w wrappers).
+// QT == 1 (Nq <= 128 or head dim 160): one query tile, warps 0/1 = TMA / MMA, warps 2..5 softmax, S double-buffered.
 //
-// Q/K/V are read in place from (lane, token, channel) tensors; a head's [tokens x d] slice is fetched
-// as ceil(d/64) swizzle-128B atoms of 64 channels starting at channel h*d.  Channels past d inside the
-// last atom belong to the next head (or are TMA zero fill): they are neutralised by zeroing the padded
-// Q chunk in smem (QK^T) and by never storing the corresponding O columns (PV).
+// Q/K/V are read in place from (lane, token, channel) tensors; a head's [tokens x d] slice is fetched as
+// ceil(d/64) swizzle-128B atoms of 64 channels starting at channel h*d.  Channels past d inside the last atom
+// belong to the next head (or are TMA zero fill): they are neutralised by zeroing the padded Q chunk in smem
+// (QK^T) and by never storing the corresponding O columns (PV).
 #include <type_traits>
 
 #include "common.cuh"
