@@ -54,12 +54,15 @@ struct AttnKParams {
 //   QT == 1: S double-buffered (QK^T of tile j+1 overlaps the softmax of tile j); any head dim <= 192.
 //   QT == 2: two query tiles ping-pong on the tensor core, one S buffer each, two softmax warpgroups
 //            (2 warps per SM sub-partition keep the MUFU pipe busy), K/V tiles fetched once for both.
-template <int D, int QT>
+//   SHORT   : QT == 1 specialisation for Nk <= 128 (the 77-token text cross-attention): one KV tile, so one S buffer,
+//             2 smem slots and 256 TMEM columns suffice and two CTAs share an SM (their load / MMA / softmax
+//             latencies overlap; a single-tile CTA is pure latency).
+template <int D, int QT, bool SHORT = false>
 struct AttnCfg {
   static constexpr int NA = (D + 63) / 64;  // 64-channel atoms per tile
   static constexpr int KQ = (D + 15) / 16;  // k-steps of Q K^T
   static constexpr int kTileBytes = NA * kAtomBytes;
-  static constexpr int kSlots = (QT == 2) ? (NA == 1 ? 8 : 4) : (NA == 1 ? 8 : (NA == 2 ? 5 : 3));
+  static constexpr int kSlots = SHORT ? 2 : ((QT == 2) ? (NA == 1 ? 8 : 4) : (NA == 1 ? 8 : (NA == 2 ? 5 : 3)));
   static constexpr int kFirstSoftmaxWarp = (QT == 2) ? 4 : 2;  // QT == 2: warpgroup 0 = {TMA, MMA, 2 idle}
   static constexpr int kThreads = 32 * kFirstSoftmaxWarp + 128 * QT;
   static constexpr int kSmemBytes = kTileBytes * (QT + kSlots) + 1024 + 256;
@@ -69,9 +72,11 @@ struct AttnCfg {
   //   columns: S_t at t*128 | P_t at 256 + t*64 | O_t at 384 + t*64
   static constexpr bool kSepP = (QT == 2 && NA == 1);
   static constexpr int kColP = 256;
-  static constexpr int kColO = kSepP ? 384 : 256;
-  static constexpr int kTmemCols = 512;
+  static constexpr int kColO = SHORT ? 128 : (kSepP ? 384 : 256);
+  static constexpr int kTmemCols = SHORT ? 256 : 512;
+  static constexpr int kMinCtas = SHORT ? 2 : 1;
   static_assert(QT == 1 || NA <= 2, "two query tiles need 2 x 64*NA O columns next to 256 S columns");
+  static_assert(!SHORT || (QT == 1 && NA <= 2), "SHORT: one query tile, S 128 + O <= 128 TMEM columns");
 };
 
 #define SG_TS(slot)                                                                                   \
@@ -81,9 +86,10 @@ struct AttnCfg {
 
 // DBG: the clock64 timeline of CTA (0,0,0) (sg_attn_args.debug_timeline) is a separate instantiation, so that the
 // production kernels carry no stamp code in their inner loops.
-template <int D, int QT, bool DBG = false>
-__global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const __grid_constant__ AttnKParams p) {
-  using Cfg = AttnCfg<D, QT>;
+template <int D, int QT, bool DBG = false, bool SHORT = false>
+__global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT, SHORT>::kMinCtas)
+    attn_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = AttnCfg<D, QT, SHORT>;
   constexpr int NA = Cfg::NA;
   constexpr int kSlots = Cfg::kSlots;
   extern __shared__ uint8_t smem_raw[];
@@ -463,6 +469,21 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
           }
         }
         SG_TS(5);
+      } else if constexpr (SHORT) {
+        // single KV tile: no previous PV to overlap, P (aliasing S, which is in registers) is stored chunk by chunk
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 x = ffma2(make_float2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sc2, nm2);
+            const float e0 = fast_exp2(x.x);
+            const float e1 = fast_exp2(x.y);
+            sum2[(i >> 1) & 3] = fadd2(sum2[(i >> 1) & 3], make_float2(e0, e1));
+            pk[i >> 1] = pack_bf16x2(e0, e1);
+          }
+          tmem_st16(s_tmem + c * 16, pk);
+        }
       } else {
         uint32_t pk[2][32];
 #pragma unroll
@@ -532,21 +553,21 @@ __global__ void __launch_bounds__(AttnCfg<D, QT>::kThreads, 1) attn_kernel(const
   }
 }
 
-template <int D, int QT, bool DBG = false>
+template <int D, int QT, bool DBG = false, bool SHORT = false>
 static int launch_attn(const AttnKParams& kp, int nq, int heads, int lanes, cudaStream_t stream) {
-  using Cfg = AttnCfg<D, QT>;
+  using Cfg = AttnCfg<D, QT, SHORT>;
   if constexpr (!DBG && D == 40 && QT == 2) {
     if (kp.dbg != nullptr) return launch_attn<D, QT, true>(kp, nq, heads, lanes, stream);  // bring-up timeline build
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<D, QT, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<D, QT, DBG, SHORT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
   dim3 grid((nq + 128 * QT - 1) / (128 * QT), heads, lanes);
-  attn_kernel<D, QT, DBG><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
+  attn_kernel<D, QT, DBG, SHORT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -555,6 +576,7 @@ static int launch_attn(const AttnKParams& kp, int nq, int heads, int lanes, cuda
 template <int D>
 static int launch_attn_auto(const AttnKParams& kp, int nq, int heads, int lanes, cudaStream_t stream) {
   if constexpr (D <= 128) {
+    if (kp.nk <= 128) return launch_attn<D, 1, false, true>(kp, nq, heads, lanes, stream);  // text cross-attention
     if (nq > 128) return launch_attn<D, 2>(kp, nq, heads, lanes, stream);
   }
   return launch_attn<D, 1>(kp, nq, heads, lanes, stream);
