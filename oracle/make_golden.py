@@ -114,20 +114,22 @@ def main():
     with open(os.path.join(GOLD, "scheduler.json"), "w") as f:
         json.dump(out, f)
 
-    # ---- full pipeline call with stubs --------------------------------------------------------------
-    sch2 = DDIM(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000,
-                set_alpha_to_one=False, steps_offset=1, clip_sample=False)
-    pipe = Pipe(vae=StubVAE(), text_encoder=StubTextEncoder(TINY_CONFIG["cross_attention_dim"]),
-                tokenizer=StubTokenizer(), unet=ref, scheduler=sch2)
-    lat_steps = []
-    torch.manual_seed(1234)  # global RNG: VAE posterior samples + the shared `noise` tensor
-    gen = torch.Generator("cpu").manual_seed(99)
-    res = pipe(image_prompt=pipeline_images(), generator=gen, output_type="np",
-               callback=lambda i, t, lat: lat_steps.append(lat.clone()), **PIPE_ARGS)
-    assert len(lat_steps) == 2, len(lat_steps)
-    torch.save(dict(latents_step=[l.clone() for l in lat_steps], global_seed=1234, gen_seed=99, image_seed=5,
-                    text_seed=7), os.path.join(GOLD, "pipeline_tiny.pt"))
-    print("pipeline_tiny: final latent std %.4f" % lat_steps[-1].std())
+    # ---- full pipeline call with stubs, both stages that condition on prior frames -------------------
+    # (model/pipeline.py:419-436: the stages differ only in the timesteps the frames are noised to)
+    for stage, fname in (("auto-regressive", "pipeline_tiny.pt"), ("multi-image-condition", "pipeline_tiny_mic.pt")):
+        sch2 = DDIM(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000,
+                    set_alpha_to_one=False, steps_offset=1, clip_sample=False)
+        pipe = Pipe(vae=StubVAE(), text_encoder=StubTextEncoder(TINY_CONFIG["cross_attention_dim"]),
+                    tokenizer=StubTokenizer(), unet=ref, scheduler=sch2)
+        lat_steps = []
+        torch.manual_seed(1234)  # global RNG: VAE posterior samples + the shared `noise` tensor
+        gen = torch.Generator("cpu").manual_seed(99)
+        pipe(image_prompt=pipeline_images(), generator=gen, output_type="np",
+             callback=lambda i, t, lat: lat_steps.append(lat.clone()), **dict(PIPE_ARGS, stage=stage))
+        assert len(lat_steps) == 2, len(lat_steps)
+        torch.save(dict(latents_step=[l.clone() for l in lat_steps], global_seed=1234, gen_seed=99, image_seed=5,
+                        text_seed=7, stage=stage), os.path.join(GOLD, fname))
+        print("%s (%s): final latent std %.4f" % (fname, stage, lat_steps[-1].std()))
     for fn in sorted(os.listdir(GOLD)):
         print("  ", fn, os.path.getsize(os.path.join(GOLD, fn)), "bytes")
 

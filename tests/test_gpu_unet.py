@@ -167,3 +167,25 @@ def test_pipeline_call_matches_reference_pipeline_golden(tiny):
     res = pipe(image_prompt=pipeline_images(g["image_seed"]).cuda(), output_type="np", **PIPE_ARGS)
     img = res.images
     assert img.shape == (1, 512, 512, 3) and bool((img == img).all())
+
+
+def test_multi_image_condition_stage_matches_reference_golden(tiny):
+    """Second frame-conditioned stage (every prior frame noised to ref_t, model/pipeline.py:422-424,432-433) vs the
+    latents of the REFERENCE pipeline (tests/golden/pipeline_tiny_mic.pt); kept last in the GPU suite."""
+    from oracle.make_golden import PIPE_ARGS
+    from oracle.stubs import StubTextEncoder, StubTokenizer, StubVAE
+    from test_oracle import stub_pipeline_inputs
+    _, mod = tiny
+    g = torch.load(os.path.join(GOLD, "pipeline_tiny_mic.pt"))
+    assert g["stage"] == "multi-image-condition"
+    pipe = StableDiffusionPipeline(StubVAE().cuda(), StubTextEncoder(TINY_CONFIG["cross_attention_dim"], g["text_seed"]).cuda(),
+                                   StubTokenizer(), mod, DDIMScheduler())
+    inp = stub_pipeline_inputs(g, TINY_CONFIG["cross_attention_dim"])
+    cu = {k: ([t.cuda() for t in v] if isinstance(v, list) else v.cuda()) for k, v in inp.items()}
+    lat = []
+    pipe.denoise(num_inference_steps=PIPE_ARGS["num_inference_steps"], guidance_scale=PIPE_ARGS["guidance_scale"],
+                 image_guidance_scale=PIPE_ARGS["image_guidance_scale"], stage="multi-image-condition",
+                 callback=lambda s, t, l: lat.append(l.clone()), **cu)
+    assert len(lat) == len(g["latents_step"])
+    for got, ref in zip(lat, g["latents_step"]):
+        check(got, ref, rel=0.15, what="multi-image-condition latents")

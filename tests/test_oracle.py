@@ -92,13 +92,17 @@ def stub_pipeline_inputs(g, xdim):
                 prev_cond=prev_cond, frame_latents=frame_latents, zero_latents=zero, noise=noise)
 
 
-def test_denoise_loop_matches_reference_pipeline_golden(tiny_oracle):
-    g = torch.load(os.path.join(GOLD, "pipeline_tiny.pt"))
+@pytest.mark.parametrize("fname,stage", [("pipeline_tiny.pt", "auto-regressive"),
+                                         ("pipeline_tiny_mic.pt", "multi-image-condition")])
+def test_denoise_loop_matches_reference_pipeline_golden(tiny_oracle, fname, stage):
+    """Both frame-conditioned stages of the reference's StableDiffusionPipeline.__call__ (model/pipeline.py:419-436)."""
+    g = torch.load(os.path.join(GOLD, fname))
+    assert g["stage"] == stage
     inp = stub_pipeline_inputs(g, TINY_CONFIG["cross_attention_dim"])
     steps = []
     out = sampler.denoise(tiny_oracle, num_inference_steps=PIPE_ARGS["num_inference_steps"],
                           guidance_scale=PIPE_ARGS["guidance_scale"], image_guidance_scale=PIPE_ARGS["image_guidance_scale"],
-                          stage=PIPE_ARGS["stage"], callback=lambda t, lat: steps.append(lat.clone()), **inp)
+                          stage=stage, callback=lambda t, lat: steps.append(lat.clone()), **inp)
     assert len(steps) == len(g["latents_step"])
     for a, b in zip(steps, g["latents_step"]):
         assert (a - b).abs().max() < 5e-4 * max(1.0, float(b.abs().max()))
