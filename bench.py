@@ -3,8 +3,10 @@
 
   python bench.py --gpus N --steps K --warmup W            # this framework (sm_100a kernels)
   python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host CPU cores
+  python bench.py --sweep [--gpus N]                       # BASELINE cfg5: R in {1,3,5} x {512,768} px
+  python bench.py --batch 8 --gpus 8                       # BASELINE cfg4: global batch 64
 
-Workload (config.workload): SD-1.5-shaped UNet + StoryGen attn3 (909 M params, seeded random weights —
+Workload (config.workload): SD-1.5-shaped UNet + StoryGen attn3 (909 M params, name-seeded random weights —
 no checkpoint exists offline), 512x512 (latent 64x64), 3 prior frames, 50 DDIM steps, dual guidance,
 bf16 storage / fp32 accumulation, B images per GPU ("cfg2", B=4).  ONE bench step = one full 50-step
 generation of B images on every rank (weak scaling) followed by the single NCCL all-gather of the
@@ -14,12 +16,19 @@ final latents; value = images / second over all ranks.  Inputs are synthetic lat
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
 One step streams ~1.8 GB of weights and several GB of activations through a 126 MB L2 200 times, so
 no explicit L2 flush is needed ("inputs larger than L2").
+
+Roofline: `roofline` describes the kernel with the LARGEST share of a denoising step (profiles/r02_kernel_shares.json,
+made from the committed ncu launch list; today attn_kernel<40,2>), timed live with CUDA events in this run;
+`roofline_detail.model` is computed from the FLOPs this path EXECUTES (the duplicate CFG lane of the feature passes
+and its attn3 K/V projection are not executed and not credited); the reference-equivalent figure is reported
+separately as a speed-up factor.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -32,11 +41,25 @@ if ROOT not in sys.path:
 # algorithmic work of the reference path (2*MAC, per CFG lane, latent 64x64)
 GF_FEATURE_PASS = 803.3
 GF_DENOISE_PASS = {1: 976.9, 3: 1273.1, 5: 1569.3}
+GF_ATTN3_KV_PROJ_PER_FRAME = 25.6  # attn3 to_k/to_v over one prior frame's 16 tapped maps, per K/V lane
 
 
-def tflop_per_image(R: int, steps: int) -> float:
-    den = GF_DENOISE_PASS.get(R, 976.9 + (R - 1) * 148.1)
-    return 3 * steps * (R * GF_FEATURE_PASS + den) / 1e3
+def gf_denoise(R: int) -> float:
+    return GF_DENOISE_PASS.get(R, 976.9 + (R - 1) * 148.1)
+
+
+def tflop_per_image_reference(R: int, steps: int) -> float:
+    """What the reference executes: 3 CFG lanes x [R feature passes + 1 denoise pass] per step."""
+    return 3 * steps * (R * GF_FEATURE_PASS + gf_denoise(R)) / 1e3
+
+
+def tflop_per_image_executed(R: int, steps: int) -> float:
+    """What THIS path executes per image: feature passes on 2 of the 3 CFG lanes (the third duplicates the second,
+    model/pipeline.py:429-430), 3 denoise lanes of which two share one attn3 K/V projection (kv_map)."""
+    feature_lanes, denoise_lanes, kv_lanes = 2, 3, 2
+    per_step = feature_lanes * R * GF_FEATURE_PASS + denoise_lanes * gf_denoise(R) \
+        - (denoise_lanes - kv_lanes) * R * GF_ATTN3_KV_PROJ_PER_FRAME
+    return steps * per_step / 1e3
 
 
 def load_peaks():
@@ -46,6 +69,14 @@ def load_peaks():
             d = json.load(f)
         return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def load_json(rel):
+    p = os.path.join(ROOT, rel)
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
 
 
 class ClockSampler:
@@ -100,62 +131,98 @@ def usable_cores() -> int:
 class CpuReference:
     """The reference's algorithm on the host cores: the fp32 oracle (asserted equal to the reference's
     model/*.py in tests/test_oracle.py; the reference itself needs diffusers==0.13.1, absent offline).
-    One SAMPLE = one feature-pass UNet call + one denoise-pass UNet call (R prior frames) for ONE CFG lane
-    (0.80 + 1.27 TFLOP at R=3).  A denoising step of one image is 3 lanes x (R feature + 1 denoise) calls,
-    every lane independent, so  t_step = 3 * (R * t_feature + t_denoise)  and images/s = 1 / (steps * t_step).
-    Attention uses SDPA (same math as the default baddbmm path, without materialising 4.8 GB of scores)."""
 
-    def __init__(self, R: int, threads: int):
+    The unit of work is ONE UNet call of a full denoising step of ONE image (B = 1): the 3 CFG lanes batched into
+    one call, exactly as model/pipeline.py:418-453 issues them — R feature-pass calls (one per prior frame, each
+    noised to its own timestep) and 1 denoise-pass call conditioned on the R x 16 tapped feature maps.  A bench
+    "step" of the reference arm is one such call, cycling  denoise, feature_0 .. feature_{R-1}; R + 1 consecutive
+    steps are one complete denoising step (11.05 TFLOP at R = 3).  images/s = 1 / (ddim_steps x t_step) with
+    t_step = R x median(feature call) + median(denoise call).
+    Attention: torch SDPA (same math as the reference's default baddbmm -> softmax -> bmm path, without
+    materialising 4.8 GB of scores per L0 attn3 call)."""
+
+    def __init__(self, R: int, threads: int, latent: int = 64):
         import torch
 
         from oracle import sampler
         from oracle.unet import SD15_CONFIG, OracleUNet
-        self.torch, self.R = torch, R
+        from oracle.weights import load_seeded
+        self.torch, self.R, self.sampler = torch, R, sampler
         torch.set_num_threads(threads)
-        torch.manual_seed(0)
-        with torch.no_grad():
-            self.net = OracleUNet(**SD15_CONFIG).eval()
-        self.inp = sampler.synthetic_inputs(1, R)
+        torch.set_grad_enabled(False)
+        self.net = load_seeded(OracleUNet(**SD15_CONFIG).eval(), 0)
+        self.inp = sampler.synthetic_inputs(1, R, latent_hw=latent)
         self.acp = sampler.alphas_cumprod()
-        self.sampler = sampler
+        self.t = sampler.ddim_timesteps(50)[0]
+        self.taps = None
 
-    def sample_seconds(self):
+    def feature_call(self, i: int) -> float:
         torch, inp, s = self.torch, self.inp, self.sampler
-        with torch.no_grad():
-            t0 = time.perf_counter()
-            ft = s.feature_timesteps(981, self.R, "auto-regressive")[0]
-            x = s.add_noise(inp["frame_latents"][0], inp["noise"], torch.full((1,), ft, dtype=torch.long), self.acp)
-            taps = self.net(x, ft, inp["prev_cond"][0], None)[1]
-            t_feat = time.perf_counter() - t0
-            img = {k: torch.cat([v] * self.R, 1) for k, v in taps.items()}
-            t0 = time.perf_counter()
-            self.net(inp["latents"], 981, inp["text_cond"], img)
-            t_den = time.perf_counter() - t0
-        return t_feat, t_den
+        ft = s.feature_timesteps(self.t, self.R, "auto-regressive")[i]
+        t0 = time.perf_counter()
+        tt = torch.full((1,), ft, dtype=torch.long)
+        noisy_frame = s.add_noise(inp["frame_latents"][i], inp["noise"], tt, self.acp)
+        noisy_zero = s.add_noise(inp["zero_latents"], inp["noise"], tt, self.acp)
+        x = torch.cat([noisy_zero, noisy_frame, noisy_frame])
+        txt = torch.cat([inp["prev_uncond"][i], inp["prev_cond"][i], inp["prev_cond"][i]])
+        taps = self.net(x, ft, txt, None)[1]
+        dt = time.perf_counter() - t0
+        if self.taps is None:
+            self.taps = taps
+        return dt
 
-    def describe(self, t_feat, t_den, ddim_steps, n):
-        t_step = 3 * (self.R * t_feat + t_den)
-        return t_step, (f"{n} x [one feature-pass + one denoise-pass UNet call, 1 CFG lane, R={self.R}: "
-                        f"{t_feat:.2f} s + {t_den:.2f} s]; t_step = 3 lanes x (R x feature + denoise) = {t_step:.1f} s; "
-                        f"images/s = 1/({ddim_steps} x t_step); fp32 oracle == reference model/*.py, SDPA attention")
+    def denoise_call(self) -> float:
+        torch, inp = self.torch, self.inp
+        if self.taps is None:
+            self.feature_call(0)
+        img = {k: torch.cat([v] * self.R, 1) for k, v in self.taps.items()}  # shapes of the real step; values irrelevant
+        t0 = time.perf_counter()
+        txt = torch.cat([inp["text_uncond"], inp["text_uncond"], inp["text_cond"]])
+        self.net(torch.cat([inp["latents"]] * 3), self.t, txt, img)
+        return time.perf_counter() - t0
+
+    def call(self, k: int):
+        """k-th call of the cycle: denoise, feature_0, ..., feature_{R-1}."""
+        i = k % (self.R + 1)
+        return ("denoise", self.denoise_call()) if i == 0 else ("feature", self.feature_call(i - 1))
+
+    def describe(self, tf, td, ddim_steps):
+        t_step = self.R * statistics.median(tf) + statistics.median(td)
+        return t_step, (f"B=1 denoising step as the reference issues it: {len(tf)} feature-pass + {len(td)} denoise-pass UNet "
+                        f"calls at 3 CFG lanes (R={self.R}); median {statistics.median(tf):.2f} s / {statistics.median(td):.2f} s per call; "
+                        f"t_step = R x feature + denoise = {t_step:.1f} s; images/s = 1/({ddim_steps} x t_step); "
+                        "fp32 oracle == reference model/*.py, SDPA attention")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = usable_cores()
-    ref = CpuReference(args.frames, threads)
-    if args.warmup > 0:
-        ref.sample_seconds()
-    ts = [ref.sample_seconds() for _ in range(args.steps)]
-    t_feat, t_den = sum(t[0] for t in ts) / len(ts), sum(t[1] for t in ts) / len(ts)
-    t_step, desc = ref.describe(t_feat, t_den, args.ddim_steps, len(ts))
+    ref = CpuReference(args.frames, threads, args.latent)
+    for k in range(args.warmup):
+        ref.call(k)
+    tf, td, wall = [], [], 0.0
+    for k in range(args.steps):
+        kind, dt = ref.call(k)
+        (td if kind == "denoise" else tf).append(dt)
+        wall += dt
+    extra = []
+    if not tf:  # K too small to contain both kinds: one extra sample, reported, outside the K timed steps
+        tf.append(ref.feature_call(0))
+        extra.append("feature")
+    if not td:
+        td.append(ref.denoise_call())
+        extra.append("denoise")
+    t_step, desc = ref.describe(tf, td, args.ddim_steps)
+    if extra:
+        desc += f"; extra untimed-in-K samples: {extra}"
     value = 1.0 / (args.ddim_steps * t_step)
     line = {
         "impl": "reference", "metric": "images_per_sec_512px_3ref_50step", "value": value, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * args.ddim_steps * t_step * args.batch,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
+        "step_definition": "one UNet call (3 CFG lanes) of a B=1 denoising step, cycling denoise, feature_0..feature_{R-1}",
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -164,173 +231,302 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, world):
+    cfg = "cfg2" if args.batch == 4 else ("cfg4" if args.batch == 8 else f"B={args.batch}")
     return {"workload": f"StoryGen denoise loop: SD-1.5 UNet+attn3 (909M), {8 * args.latent}px, {args.frames} prior "
                         f"frames, {args.ddim_steps} DDIM steps, dual CFG (3 lanes), B={args.batch} images/GPU "
-                        "(BASELINE cfg2); tokenizer/CLIP/VAE excluded (synthetic latents+embeddings)",
+                        f"(BASELINE {cfg}); tokenizer/CLIP/VAE excluded (synthetic latents+embeddings)",
             "global_batch": args.batch * world, "per_gpu_batch": args.batch, "prior_frames": args.frames,
             "ddim_steps": args.ddim_steps, "latent": args.latent, "parallelism": f"dp{world} (batch shard, 1 all-gather)",
             "l2": "working set per step >> 126 MB L2 (no flush needed)"}
 
 
-def kernel_rooflines(torch, peaks, lanes):
-    """Live CUDA-event timing of the dominant kernels in isolation (burst peak as denominator)."""
+# ------------------------------------------------------------------------------------------------------------------
+# live kernel timings (CUDA events on torch's current stream = the stream the kernels are launched on)
+# ------------------------------------------------------------------------------------------------------------------
+def _timeit(torch, fn, n_buf, iters=10):
+    for i in range(3):
+        fn(i % n_buf)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % n_buf)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def time_attention(torch, lanes, heads, hd, nq, nk, iters=6):
+    """One attention-core launch: (seconds, flops, algorithmic bytes)."""
+    from storygen_b200 import ops
+    from storygen_b200.ops import BF16
+    c = heads * hd
+    q = torch.randn(lanes, nq, c, device="cuda").to(BF16)
+    k = torch.randn(lanes, nk, c, device="cuda").to(BF16)
+    v = torch.randn(lanes, nk, c, device="cuda").to(BF16)
+    o = torch.empty(lanes, nq, c, device="cuda", dtype=BF16)
+    t = _timeit(torch, lambda i: ops.attention(q, k, v, o, lanes, heads, hd, nq, nk, (nq * c, c), (nk * c, c), (nk * c, c)), 1, iters)
+    return t, 4.0 * lanes * nq * nk * c, (2 * nq + 2 * nk) * c * 2.0 * lanes
+
+
+def kernel_rooflines(torch, peaks, B, R, latent, ms_per_denoising_step):
+    """Live timing of the dominant kernels in isolation (burst peak as denominator).  Shares are isolated-kernel time x
+    launches per denoising step / measured step time; the ncu launch list under profiles/ is the authoritative split."""
     from storygen_b200 import ops
     from storygen_b200.ops import BF16, Src, taps3x3
     dev = "cuda"
     out = {}
+    hw = latent * latent
+    nf, nd = 2 * B * R, 3 * B
 
-    def timeit(fn, n_buf, iters=12):
-        for i in range(3):
-            fn(i % n_buf)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(iters):
-            fn(i % n_buf)
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / iters * 1e-3
+    # ---- attn_kernel<40,2>: the L0 attention cores of a step (5 transformer blocks at L0 per UNet call)
+    shapes = [("attn3 image cross-attention, denoise pass", nd, hw, R * hw, 5),
+              ("attn1 self-attention, feature pass", nf, hw, hw, 5),
+              ("attn1 self-attention, denoise pass", nd, hw, hw, 5)]
+    t_sum = f_sum = b_sum = 0.0
+    per_shape = []
+    for name, lanes, nq, nk, count in shapes:
+        t, fl, by = time_attention(torch, lanes, 8, 40, nq, nk)
+        per_shape.append({"shape": name, "lanes": lanes, "nq": nq, "nk": nk, "launches_per_step": count,
+                          "ms_per_launch": t * 1e3, "tflops": fl / t / 1e12, "algorithmic_gbs": by / t / 1e9})
+        t_sum += count * t
+        f_sum += count * fl
+        b_sum += count * by
+    ncu = load_json("profiles/r02_ncu_attn40.json") or {}
+    out["attn_kernel<40,2>"] = {
+        "bound": "tensor", "achieved": f_sum / t_sum / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+        "frac": f_sum / t_sum / 1e12 / peaks["tf_burst"], "traffic": ncu.get("dram_bytes_per_launch"),
+        "share_of_step": t_sum * 1e3 / ms_per_denoising_step, "launches_per_step": 15,
+        "attn_tc_util_pct": 100.0 * f_sum / t_sum / 1e12 / peaks["tf_burst"],
+        "tensor_pipe_pct": ncu.get("tensor_pipe_pct"), "xu_pipe_pct": ncu.get("xu_pipe_pct"),
+        "ncu_source": ncu.get("source"), "algorithmic_gbs": b_sum / t_sum / 1e9, "shapes": per_shape,
+        "note": "d=40 attention is exp-unit bound, not tensor bound: a 128x128 score tile needs 16384 exp2 (MUFU 16/clk/SM "
+                "= 1024 clk) against ~580 clk of tcgen05 math; achieved/peak is therefore reported against the bf16 tensor "
+                "peak as the metric asks (attn TC-util), with the XU / tensor pipe percentages of the ncu capture beside it"}
 
-    # (1) L0 ResBlock conv: 3x3, 320 -> 320 at 64x64 over `lanes` images (the most frequent heavy GEMM);
-    #     4 rotating input/output pairs (4 x 2 x 63 MB at 24 lanes) so that L2 does not hold them
-    c, h, w = 320, 64, 64
+    # ---- L0 ResBlock conv 3x3 320 -> 320 over the feature-pass lanes (most frequent heavy GEMM, gemm_kernel<160,0>)
+    c, h, w, lanes = 320, latent, latent, nf
     xs = [torch.randn(lanes, h, w, c, device=dev).to(BF16) for _ in range(4)]
     ys = [torch.empty(lanes, h, w, c, device=dev, dtype=BF16) for _ in range(4)]
     wt = (torch.randn(c, 9 * c, device=dev) * (9 * c) ** -0.5).to(BF16)
     b = torch.zeros(c, device=dev)
-    t = timeit(lambda i: ops.gemm([Src.nhwc(xs[i])], taps3x3(0, c), (w, h, lanes), wt, ys[i], bias=b), 4)
+    t = _timeit(torch, lambda i: ops.gemm([Src.nhwc(xs[i])], taps3x3(0, c), (w, h, lanes), wt, ys[i], bias=b), 4, 12)
     flops = 2.0 * lanes * h * w * c * 9 * c
-    # traffic = dram__bytes_read.sum + dram__bytes_write.sum of this kernel inside a step at 24 lanes (ncu --set full,
-    # profiles/r01_final_ncu_full_conv.csv): 64.9 MB read + 17.5 MB written < 127.7 MB algorithmic (part of the output is still in L2 at kernel end)
-    traffic = 82338816 if lanes == 24 else None
+    ncu_c = load_json("profiles/r02_ncu_conv320.json") or {}
     out["conv3x3_320_L0"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                             "frac": flops / t / 1e12 / peaks["tf_burst"], "traffic": traffic,
+                             "frac": flops / t / 1e12 / peaks["tf_burst"], "traffic": ncu_c.get("dram_bytes_per_launch"),
                              "algorithmic_bytes": 2 * lanes * h * w * c * 2 + 9 * c * c * 2,
-                             "note": "N = 320 runs as two 160-wide tiles: per 64-deep k-block a CTA pulls A 16 KB + B 20 KB into shared "
-                                     "memory for 4 x 80 clk of tcgen05 math = 115 B/clk/SM demanded vs ~80-100 B/clk/SM that TMA delivers "
-                                     "from L2 with all SMs active (profiles/r01_ubench_tma_ingest.log): operand-ingest bound, not "
-                                     "issue bound (issue streams run at the math rate: profiles/r01_ubench_issue_stream.log)",
-                             "flops_per_launch": flops, "ms_per_launch": t * 1e3, "lanes": lanes}
-    # (2) L0 image cross-attention core: Nq = 4096, Nk = 3 * 4096, 8 heads x d40
-    hd, heads, nq, nk = 40, 8, 4096, 3 * 4096
-    ql = max(3, lanes // 2)
-    q = torch.randn(ql, nq, c, device=dev).to(BF16)
-    k = torch.randn(ql, nk, c, device=dev).to(BF16)
-    v = torch.randn(ql, nk, c, device=dev).to(BF16)
-    o = torch.empty(ql, nq, c, device=dev, dtype=BF16)
-    t = timeit(lambda i: ops.attention(q, k, v, o, ql, heads, hd, nq, nk, (nq * c, c), (nk * c, c), (nk * c, c)), 1, iters=6)
-    flops = 4.0 * ql * nq * nk * c
-    out["attn3_core_L0"] = {"bound": "tensor", "achieved": flops / t / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                            "frac": flops / t / 1e12 / peaks["tf_burst"], "traffic": None, "flops_per_launch": flops,
-                            "ms_per_launch": t * 1e3, "lanes": ql,
-                            "note": "d=40: a 128x128 tile needs 16384 exp2 = 1024 clk of MUFU (16/clk/SM; 896 clk with 1 in 8 exps "
-                                    "on the FMA pipe) but only ~580 clk of tensor pipe (3 QK^T + 8 PV MMAs): exp-unit bound; ncu: "
-                                    "XU pipe 68 %, measured ~1450 SM-clk per tile"}
-    del xs, ys, q, k, v, o
+                             "tensor_pipe_pct": ncu_c.get("tensor_pipe_pct"), "flops_per_launch": flops,
+                             "ms_per_launch": t * 1e3, "lanes": lanes}
+    del xs, ys
     torch.cuda.empty_cache()
     return out
+
+
+def eager_unet_latency(torch, unet, B, R, latent, dev):
+    """Latency of the drop-in `unet(...)` call WITHOUT the pipeline's CUDA graph (what a caller of the class surface
+    gets): the feature pass over 2BR lanes and the denoise pass over 3B lanes of a step."""
+    g = torch.Generator("cpu").manual_seed(9)
+    nf, nd = 2 * B * R, 3 * B
+    xf = torch.randn(nf, 4, latent, latent, generator=g).to(dev)
+    tf = torch.randn(nf, 77, 768, generator=g).to(dev)
+    xd, td = xf[:nd].contiguous(), tf[:nd].contiguous()
+
+    def once(fn):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3
+
+    taps = unet(xf, 500, tf, return_dict=False)[1]
+    cond = {k: v.view(2 * B, -1, v.shape[-1])[B:].repeat(3, 1, 1)[:nd].contiguous() for k, v in taps.items()}
+    ms_f = once(lambda: unet(xf, 500, tf, return_dict=False))
+    ms_d = once(lambda: unet(xd, 500, td, image_hidden_states=cond, return_dict=False))
+    return {"feature_pass_ms": ms_f, "feature_lanes": nf, "denoise_pass_ms": ms_d, "denoise_lanes": nd,
+            "note": "host-synchronous wall time of one eager call (tensor maps re-encoded per launch, caching allocator)"}
+
+
+def build_model(torch, dev):
+    from storygen_b200 import UNet2DConditionModel
+    from storygen_b200.synthetic import seeded_init_
+    with torch.device("meta"):
+        unet = UNet2DConditionModel(cross_attention_dim=768)
+    # name-seeded CPU weights (identical on every rank and in the fp32 oracle that made tests/golden/bench_steps_fp32.pt)
+    return seeded_init_(unet.to_empty(device="cpu"), seed=0).to(dev).eval()
 
 
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
-    from storygen_b200 import DDIMScheduler, StableDiffusionPipeline, UNet2DConditionModel, _lib
+    from storygen_b200 import DDIMScheduler, StableDiffusionPipeline
     from storygen_b200.distributed import gather_latents, shard_range
-    from storygen_b200.synthetic import input_bytes, random_init_, synthetic_inputs, to_device
+    from storygen_b200.synthetic import input_bytes, synthetic_inputs, to_device
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    B, R = args.batch, args.frames
-
-    with torch.device("meta"):
-        unet = UNet2DConditionModel(cross_attention_dim=768)
-    unet = random_init_(unet.to_empty(device=dev), seed=0).eval()
+    unet = build_model(torch, dev)
     pipe = StableDiffusionPipeline(None, None, None, unet, DDIMScheduler())
-    first, _ = shard_range(world * B, rank, world)
-    host_in = synthetic_inputs(B, R, latent_hw=args.latent, first_image=first, pin=True)
-    dev_in = to_device(host_in, dev)
-    kw = dict(num_inference_steps=args.ddim_steps, guidance_scale=7.0, image_guidance_scale=3.5, stage="auto-regressive")
-    host_out = torch.empty(B, 4, args.latent, args.latent).pin_memory()
 
-    def one_step(inputs, to_host):
-        lat = pipe.denoise(**inputs, **kw)
-        lat_all = gather_latents(lat, world * B)  # the path's only collective (2 MiB at 8 x B=8)
-        assert lat_all.shape[0] == world * B
-        if to_host:
-            host_out.copy_(lat, non_blocking=True)
-        return lat
+    def measure(B, R, latent, steps, warmup, with_e2e=True, sampler=None):
+        first, _ = shard_range(world * B, rank, world)
+        host_in = synthetic_inputs(B, R, latent_hw=latent, first_image=first, pin=True)
+        dev_in = to_device(host_in, dev)
+        kw = dict(num_inference_steps=args.ddim_steps, guidance_scale=7.0, image_guidance_scale=3.5, stage="auto-regressive")
+        host_out = torch.empty(B, 4, latent, latent).pin_memory()
 
-    def timed(inputs, to_host, steps):
-        if world > 1:
-            dist.barrier()
+        def one_step(inputs, to_host, callback=None):
+            lat = pipe.denoise(**inputs, **kw, callback=callback)
+            lat_all = gather_latents(lat, world * B)  # the path's only collective (2 MiB at 8 x B=8)
+            assert lat_all.shape[0] == world * B
+            if to_host:
+                host_out.copy_(lat, non_blocking=True)
+            return lat
+
+        def timed(inputs, to_host, n):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                one_step(inputs, to_host)
+            e1.record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item())
+
+        for _ in range(warmup):
+            one_step(dev_in, False)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            one_step(inputs, to_host)
-        e1.record()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        if sampler is not None:
+            sampler.start()
+        k0 = pipe.kernel_launches
+        ms = timed(dev_in, False, steps)
+        launches = pipe.kernel_launches - k0
+        ms_e2e = timed(host_in, True, steps) if with_e2e else None
+        return dict(ms=ms, ms_e2e=ms_e2e, launches=launches, one_step=one_step, dev_in=dev_in, host_in=host_in,
+                    host_out=host_out, first=first)
 
-    for _ in range(args.warmup):
-        one_step(dev_in, False)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    k0 = pipe.kernel_launches
-    ms = timed(dev_in, False, args.steps)
-    launches = pipe.kernel_launches - k0
-    ms_e2e = timed(host_in, True, args.steps)
+    if args.sweep:
+        run_sweep(args, torch, dist, measure, peaks, rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    B, R = args.batch, args.frames
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    m = measure(B, R, args.latent, args.steps, args.warmup, True, sampler)
     clocks = sampler.stop() if rank == 0 else None
-    lat = one_step(dev_in, False)
+    ms, ms_e2e = m["ms"], m["ms_e2e"]
+
+    # parity of THIS run's outputs: latents after DDIM steps 1 and 2 against the stored fp32 oracle trajectory
+    caught = []
+    lat = m["one_step"](m["dev_in"], False, callback=lambda s, t, l: caught.append(l.clone()) if s < 2 else None)
     finite = bool(torch.isfinite(lat).all().item())
+    parity = {"checked": False}
+    gold_path = os.path.join(ROOT, "tests", "golden", "bench_steps_fp32.pt")
+    if rank == 0 and os.path.exists(gold_path):
+        g = torch.load(gold_path)
+        if g["frames"] == R and g["latent"] == args.latent and g["ddim_steps"] == args.ddim_steps and g["images"] >= B \
+                and m["first"] == 0:
+            parity = {"checked": True, "fixture": "tests/golden/bench_steps_fp32.pt (fp32 oracle, oracle/make_bench_golden.py)"}
+            for s, (got, ref) in enumerate(zip(caught, g["latents_step"])):
+                ref = ref[:B].to(dev)
+                parity[f"max_abs_delta_step{s + 1}"] = float((got - ref).abs().max().item())
+                parity[f"ref_std_step{s + 1}"] = float(ref.std().item())
 
     images = world * B * args.steps
     value = images / (ms * 1e-3)
     e2e_value = images / (ms_e2e * 1e-3)
     if rank == 0:
-        roof = kernel_rooflines(torch, peaks, 2 * B * R)
-        tf_img = tflop_per_image(R, args.ddim_steps)
-        model_tf = tf_img * value / world  # per GPU, reference-equivalent FLOPs (de-duplicated lane NOT credited)
+        from storygen_b200.synthetic import input_bytes as _ib
+        ms_denoising_step = ms / args.steps / args.ddim_steps
+        roof = kernel_rooflines(torch, peaks, B, R, args.latent, ms_denoising_step)
+        shares = load_json("profiles/r02_kernel_shares.json") or {}
+        dominant = shares.get("dominant", "attn_kernel<40,2>")
+        main = dict(roof.get(dominant, roof["attn_kernel<40,2>"]))
+        if args.latent != 64:
+            raise SystemExit("the FLOP model (SURVEY.md Appendix B) is tabulated for 512 px; use --sweep for 768 px")
+        tf_exec = tflop_per_image_executed(R, args.ddim_steps)
+        tf_ref = tflop_per_image_reference(R, args.ddim_steps)
+        model_tf = tf_exec * value / world  # per GPU, EXECUTED FLOPs
+        eager = eager_unet_latency(torch, unet, B, R, args.latent, dev)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = usable_cores()
-            ref = CpuReference(R, threads)
-            t_feat, t_den = ref.sample_seconds()
-            t_step, desc = ref.describe(t_feat, t_den, args.ddim_steps, 1)
+            ref = CpuReference(R, threads, args.latent)
+            tf_, td_ = [ref.feature_call(0)], [ref.denoise_call()]
+            t_step, desc = ref.describe(tf_, td_, args.ddim_steps)
             cpu = {"value": 1.0 / (args.ddim_steps * t_step), "unit": "images/s", "cores": threads, "kind": "port",
                    "sample": desc}
-        main = dict(roof["conv3x3_320_L0"])
         line = {
             "metric": "images_per_sec_512px_3ref_50step", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world),
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": input_bytes(host_in),
-                    "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": _ib(m["host_in"]),
+                    "d2h_bytes_per_step": m["host_out"].numel() * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": m["launches"],
             "clocks": clocks,
-            "roofline": {k: main[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")},
-            "roofline_detail": {"peaks": peaks, "kernels": roof,
-                                "model": {"tflop_per_image_reference_equivalent": tf_img,
+            "roofline": {"kernel": dominant if dominant in roof else "attn_kernel<40,2>",
+                         **{k: main.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "share_of_step",
+                                                    "attn_tc_util_pct", "tensor_pipe_pct", "xu_pipe_pct")}},
+            "attn_tc_util_pct": roof["attn_kernel<40,2>"]["attn_tc_util_pct"],
+            "roofline_detail": {"peaks": peaks, "kernels": roof, "kernel_shares": shares.get("kernels"),
+                                "model": {"tflop_per_image_executed": tf_exec,
                                           "achieved_tflops_per_gpu": model_tf, "peak_sustained": peaks["tf_sust"],
-                                          "frac_of_sustained": model_tf / peaks["tf_sust"]}},
+                                          "frac_of_sustained": model_tf / peaks["tf_sust"],
+                                          "frac_of_burst": model_tf / peaks["tf_burst"],
+                                          "tflop_per_image_reference_equivalent": tf_ref,
+                                          "work_removed_speedup": tf_ref / tf_exec,
+                                          "note": "executed = 2R feature lanes + 3 denoise lanes - 1 shared attn3 K/V projection "
+                                                  "per image-step; the reference executes 3R + 3 lanes"},
+                                "ms_per_denoising_step_graph": ms_denoising_step, "eager_unet": eager},
             "cpu_baseline": cpu,
+            "parity": parity,
             "outputs_finite": finite,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_sweep(args, torch, dist, measure, peaks, rank, world):
+    """BASELINE cfg5: prior-frame count {1,3,5} x resolution {512,768}: images/s plus the L0 image cross-attention
+    core's achieved TFLOP/s (vs the tensor roofline) and algorithmic HBM GB/s, per point."""
+    points = []
+    B = args.batch
+    for latent in (64, 96):
+        for R in (1, 3, 5):
+            m = measure(B, R, latent, 1, 1, with_e2e=False)
+            row = {"prior_frames": R, "px": 8 * latent, "per_gpu_batch": B,
+                   "images_per_sec": world * B / (m["ms"] * 1e-3), "ms_per_generation": m["ms"], "gpu_launches": m["launches"]}
+            if rank == 0:
+                hw = latent * latent
+                t, fl, by = time_attention(torch, 3 * B, 8, 40, hw, R * hw, iters=3)
+                row["attn3_L0_core"] = {"lanes": 3 * B, "nq": hw, "nk": R * hw, "ms": t * 1e3, "tflops": fl / t / 1e12,
+                                        "frac_of_bf16_peak": fl / t / 1e12 / peaks["tf_burst"],
+                                        "algorithmic_hbm_gbs": by / t / 1e9, "hbm_frac": by / t / 1e9 / peaks["hbm"]}
+                tf_exec = tflop_per_image_executed(R, args.ddim_steps)
+                if latent == 64:
+                    row["model_tflops_executed_per_gpu"] = tf_exec * row["images_per_sec"] / world
+            points.append(row)
+            torch.cuda.empty_cache()
+    if rank == 0:
+        print(json.dumps({"metric": "sweep_images_per_sec", "unit": "images/s", "n_gpus": world, "dtype": "bf16",
+                          "data": "synthetic", "config": {"workload": "BASELINE cfg5 sweep: R in {1,3,5} x {512,768} px, "
+                                                          f"{args.ddim_steps} DDIM steps, B={B}/GPU", "peaks": peaks},
+                          "sweep": points}), flush=True)
 
 
 def main():
@@ -339,10 +535,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="images per GPU (cfg2: 4)")
+    ap.add_argument("--batch", type=int, default=4, help="images per GPU (cfg2: 4; cfg4: 8)")
     ap.add_argument("--frames", type=int, default=3)
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--sweep", action="store_true", help="BASELINE cfg5: R in {1,3,5} x {512,768} px")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

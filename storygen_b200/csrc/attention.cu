@@ -7,11 +7,14 @@
 //                              softmax warps have READ S_t(j-1) [head dims <= 64: P has its own TMEM columns]
 //   warp 2      : P V issuer   O_t += P_t V_j (tcgen05.mma TS: P read from TMEM, V MN-major, N = the head's channels)
 //                              (head dims > 64: warp 1 issues both, in order)
-//   warp 3      : idle         (warps 0..3 shrink to 64 registers, the softmax warps grow to 216: setmaxnreg)
+//   warp 3      : V fixer      (head dims <= 64) writes a column of ones into channel D of every V tile, so that
+//                              column D of O accumulates the softmax row sum on the tensor core
+//                              (warps 0..3 shrink to 64 registers, the softmax warps grow to 216: setmaxnreg)
 //   warps 4..11 : softmax      one warpgroup per query tile, one thread per query row (= TMEM lane): S row in
-//                              registers (streamed: chunk c of S(j+1) replaces chunk c of S(j)), running max with
-//                              lazy rescale of the O row (only when the max grew by > 2^8), exp2 (MUFU, 1 in 8 on
-//                              the FMA pipe), row sum, P (bf16) -> TMEM, final O / l -> global
+//                              registers (streamed: chunk c of S(j+1) replaces chunk c of S(j), and its row max is
+//                              taken under the exps of S(j)), lazy rescale of the O row (only when the max grew by
+//                              > 2^8), exp2 (MUFU; a fixed subset of the pairs as a packed cubic on the FMA pipe),
+//                              P (bf16) -> TMEM, final O / l -> global
 //   All issue loops are warp-uniform with one elected lane issuing (ptx.cuh: *_w wrappers).
 // QT == 1 (Nq <= 128 or head dim 160): one query tile, warps 0/1 = TMA / MMA, warps 2..5 softmax, S double-buffered.
 //
@@ -38,6 +41,16 @@ constexpr int kHandoff = SG_ATTN_HANDOFF;
 #define SG_ATTN_POLY_EVERY 8
 #endif
 constexpr int kPolyPairs = SG_ATTN_POLY_EVERY > 0 ? SG_ATTN_POLY_EVERY / 2 : 1;
+// head dims <= 64, two query tiles (the d = 40 level, a third of a denoising step): the software-pipelined softmax loop
+#ifndef SG_ATTN2_PINGPONG
+#define SG_ATTN2_PINGPONG 0
+#endif
+constexpr bool kPingPong2 = SG_ATTN2_PINGPONG != 0;
+#ifndef SG_ATTN2_POLY_MASK
+#define SG_ATTN2_POLY_MASK 0x11
+#endif
+// bit (i % 8) set: pair i of a 32-column chunk takes both exps on the FMA pipe (0x11 = 1 in 4, 0x49 = 3 in 8, 0x55 = 1 in 2)
+constexpr unsigned kPolyMask2 = SG_ATTN2_POLY_MASK;
 constexpr int kPolyEvery = SG_ATTN_POLY_EVERY;  // 0 = all exps on MUFU; 4 = 1 in 4 on the FMA pipe; 2 = 1 in 2  // the other warpgroup may start its exps once chunk kHandoff (of 4) is issued
 
 struct AttnKParams {
@@ -65,12 +78,18 @@ struct AttnCfg {
   static constexpr int kSlots = SHORT ? 2 : ((QT == 2) ? (NA == 1 ? 8 : 4) : (NA == 1 ? 8 : (NA == 2 ? 5 : 3)));
   static constexpr int kFirstSoftmaxWarp = (QT == 2) ? 4 : 2;  // QT == 2: warpgroup 0 = {TMA, MMA, 2 idle}
   static constexpr int kThreads = 32 * kFirstSoftmaxWarp + 128 * QT;
-  static constexpr int kSmemBytes = kTileBytes * (QT + kSlots) + 1024 + 256;
+  static constexpr int kSmemBytes = kTileBytes * (QT + kSlots) + 1024 + 512;
   // kSepP (two query tiles, one 64-channel atom): P gets its own TMEM columns instead of aliasing S, so the
   // tensor core may overwrite S_t with Q K_{j+1}^T as soon as the softmax warps have READ S_t(j) -- the
   // PV_j -> QK_{j+1} -> commit -> wake-up round trip (~1200 clk measured) leaves the softmax critical path.
   //   columns: S_t at t*128 | P_t at 256 + t*64 | O_t at 384 + t*64
   static constexpr bool kSepP = (QT == 2 && NA == 1);
+  // kSumTC: the softmax denominator comes from the tensor core.  Channel D of every V tile (the first channel past
+  // the head's own, inside the same 64-channel atom) is overwritten with ones in shared memory and the P V MMA is
+  // widened to cover it, so O[:, D] = sum_k P[:, k]: 64 packed adds per row and tile leave the FMA pipe, and the
+  // lazy O rescale keeps the sum consistent for free.
+  static constexpr bool kSumTC = kSepP && (D % 64 != 0);
+  static constexpr int kOnesChunk = (D % 64) / 8;  // 16-byte chunk of the V rows that holds channel D
   static constexpr int kColP = 256;
   static constexpr int kColO = SHORT ? 128 : (kSepP ? 384 : 256);
   static constexpr int kTmemCols = SHORT ? 256 : 512;
@@ -106,7 +125,8 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
   uint64_t* p_full = s_full + 2;         // [2] softmax -> MMA
   uint64_t* o_done = p_full + 2;         // [2] MMA -> softmax (PV retired)
   uint64_t* s_free = o_done + 2;         // [2] softmax -> MMA (S row-blocks are in registers; kSepP only)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  uint64_t* v_ready = s_free + 2;        // [kSlots] V fixer -> PV issuer (kSumTC)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_ready + kSlots);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // broadcast: provably warp-uniform role index
   const int lane = threadIdx.x & 31;
@@ -120,6 +140,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+      mbar_init(&v_ready[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
@@ -189,7 +210,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
       // rounded up to the UMMA N granularity of 16 (d = 40 -> N = 48 instead of 64: fewer wasted tensor FLOPs)
       auto idesc_pv_of = [](int a) {
         const int rem = D - 64 * a;
-        const int n = rem >= 64 ? 64 : ((rem + 15) & ~15);
+        const int n = rem >= 64 ? 64 : ((rem + (Cfg::kSumTC ? 16 : 15)) & ~15);  // kSumTC: + the ones column
         return make_idesc_bf16(128, static_cast<uint32_t>(n), 0, 1);
       };
       auto qk = [&](uint32_t q_addr, uint32_t k_addr, uint32_t s_col) {
@@ -302,7 +323,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
         } else {
           for (int j = 0; j < T; ++j) {
             const int iv = 2 * j + 1;
-            mbar_wait(&kv_full[slot_of(iv)], phase_of(iv));
+            mbar_wait(Cfg::kSumTC ? &v_ready[slot_of(iv)] : &kv_full[slot_of(iv)], phase_of(iv));
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
               mbar_wait(&p_full[t], j & 1);
@@ -315,6 +336,24 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
           }
         }
       }
+    }
+  } else if (Cfg::kSumTC && warp == 3) {
+    // ===================== V fixer: ones into channel D of every V tile =====================
+    // TMA's writes are visible once kv_full completes; the generic-proxy stores below are ordered before the
+    // tensor core's reads by fence.proxy.async + the v_ready arrive the PV issuer waits for.
+    const uint4 ones = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);  // 8 x bf16 1.0
+    for (int j = 0; j < T; ++j) {
+      const int iv = 2 * j + 1, slot = iv % kSlots;
+      mbar_wait(&kv_full[slot], static_cast<uint32_t>((iv / kSlots) & 1));
+      const uint32_t tile = smem_u32(kv_smem + slot * Cfg::kTileBytes) + (D / 64) * kAtomBytes;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int row = rr * 32 + lane;
+        sts128(tile + row * 128 + ((Cfg::kOnesChunk ^ (row & 7)) << 4), ones);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&v_ready[slot]);
     }
   }
   } else {
@@ -340,43 +379,183 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
     if (lane == 0) mbar_arrive(&q_ready[tq]);
 
     float m_used = 0.f, l_run = 0.f;
+    if constexpr (Cfg::kSepP) {
+      // ------------------------------------------------------------------------------------------------------
+      // Software-pipelined online softmax (two query tiles per CTA, head dims <= 64).
+      // Invariant at the top of tile j: sv = S_t(j) in registers (ragged tail already masked), mt = its scaled row
+      // max.  Inside the exps of chunk c of tile j, chunk c-1 of S_t(j+1) -- loaded into the registers that chunk
+      // of S_t(j) just left -- is folded into the next tile's row max, so the FMNMX stream rides under the MUFU
+      // stream and no phase of the loop leaves the exp unit idle: per tile only the last chunk's 11 FMNMX3, the
+      // 8-to-1 reduction and the P hand-over remain outside the exps.  The exp2 of the pairs selected by kPolyMask2
+      // run as a packed cubic on the FMA pipe; the row sum comes from the tensor core (kSumTC).
+      // ------------------------------------------------------------------------------------------------------
+      const uint32_t s_tmem = tmem_base + lane_base + tq * 128;
+      const uint32_t p_tmem = tmem_base + lane_base + Cfg::kColP + tq * 64;
+      uint64_t* od = &o_done[tq];
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+      uint32_t sv[4][32];
+      float mxn[8];
+      auto max_reset = [&]() {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mxn[i] = -INFINITY;
+      };
+      auto max_chunk = [&](uint32_t (&v)[32]) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mxn[i & 7] = fmaxf(mxn[i & 7], __uint_as_float(v[i]));
+      };
+      auto max_final = [&]() {
+        return fmaxf(fmaxf(fmaxf(mxn[0], mxn[1]), fmaxf(mxn[2], mxn[3])),
+                     fmaxf(fmaxf(mxn[4], mxn[5]), fmaxf(mxn[6], mxn[7]))) * p.scale_log2;
+      };
+      auto mask_chunk = [&](uint32_t (&v)[32], const int c, const int valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i >= valid) v[i] = 0xff800000u;  // -inf
+      };
+      if (kPingPong2 && tq == 1) named_bar_arrive(1, 256);  // warpgroup 0 owns the exp unit first
+
+      // prologue: S_t(0) -> registers, row max
+      mbar_wait(&s_full[tq], 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[tq]);  // the tensor core may overwrite S_t with Q_t K_1^T
+      max_reset();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (T == 1 && (p.nk % 128) != 0) mask_chunk(sv[c], c, p.nk);
+        max_chunk(sv[c]);
+      }
+      float mt = max_final();
+
+      auto tile = [&](const int j, auto has_next_tag, auto mask_next_tag) {
+        constexpr bool kHasNext = decltype(has_next_tag)::value;
+        constexpr bool kMaskNext = decltype(mask_next_tag)::value;
+        SG_TS(0);
+        float alpha = 1.f;
+        bool need = false;
+        if (j == 0) {
+          m_used = mt;
+        } else if (mt > m_used + 8.f) {  // lazy: rescale O (and with it the row sum) only when the max grew by > 2^8
+          alpha = fast_exp2(m_used - mt);
+          m_used = mt;
+          need = true;
+        }
+        const float2 nm2 = make_float2(-m_used, -m_used);
+        [[maybe_unused]] const int valid_next = p.nk - (j + 1) * 128;
+        [[maybe_unused]] float2 sum2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f),
+                                           make_float2(0.f, 0.f)};
+        max_reset();
+        if (kPingPong2) named_bar_sync(1 + tq, 256);
+        SG_TS(4);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            if constexpr (kHasNext) {
+              if (c >= 1 && i == 16) {
+                // chunk c-1 of S(j+1) was requested a chunk ago: fold it into the next tile's row max
+                tmem_ld_wait();
+                if constexpr (kMaskNext) mask_chunk(sv[c - 1], c - 1, valid_next);
+                max_chunk(sv[c - 1]);
+              }
+            }
+            const float2 x = ffma2(make_float2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sc2, nm2);
+            float2 e;
+            if ((kPolyMask2 >> ((i >> 1) & 7)) & 1u) {
+              e = exp2_fma2(x);
+            } else {
+              e.x = fast_exp2(x.x);
+              e.y = fast_exp2(x.y);
+            }
+            if constexpr (!Cfg::kSumTC) sum2[(i >> 1) & 3] = fadd2(sum2[(i >> 1) & 3], e);
+            pk[i >> 1] = pack_bf16x2(e.x, e.y);
+          }
+          if (c == 0 && j > 0) {
+            // P V_{j-1} must have retired before P_j overwrites P_{j-1} and before the O row may be rescaled; its
+            // ~500 clk hide behind the first chunk of exps.  o_done phases are consumed strictly in order.
+            mbar_wait(od, (j - 1) & 1);
+            tc_fence_after();
+            if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+              for (int oc = 0; oc < 2; ++oc) {
+                uint32_t ov[32];
+                tmem_ld32(o_tmem + oc * 32, ov);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+                tmem_st32(o_tmem + oc * 32, ov);
+              }
+            }
+          }
+          tmem_st16(p_tmem + c * 16, pk);
+          if (kPingPong2 && c == kHandoff && !(tq == 1 && j == T - 1)) named_bar_arrive(2 - tq, 256);
+          if constexpr (kHasNext) {
+            if (c == 0) {
+              mbar_wait(&s_full[tq], (j + 1) & 1);
+              tc_fence_after();
+              SG_TS(1);
+            }
+            tmem_ld32(s_tmem + c * 32, sv[c]);  // S(j+1), chunk c -> the registers chunk c of S(j) just left
+          }
+        }
+        SG_TS(5);
+        if constexpr (!Cfg::kSumTC) {
+          const float2 s01 = fadd2(sum2[0], sum2[1]), s23 = fadd2(sum2[2], sum2[3]);
+          l_run = l_run * alpha + ((s01.x + s01.y) + (s23.x + s23.y));
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[tq]);
+        if constexpr (kHasNext) {
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[tq]);  // S_t(j+1) is in registers
+          if constexpr (kMaskNext) mask_chunk(sv[3], 3, valid_next);
+          max_chunk(sv[3]);
+          mt = max_final();
+        }
+        SG_TS(6);
+      };
+      const bool ragged = (p.nk % 128) != 0;
+      for (int j = 0; j + 2 < T; ++j) tile(j, std::true_type{}, std::false_type{});
+      if (T >= 2) {
+        if (ragged) tile(T - 2, std::true_type{}, std::true_type{});
+        else tile(T - 2, std::true_type{}, std::false_type{});
+      }
+      tile(T - 1, std::false_type{}, std::false_type{});
+
+      // final: O / l -> global (only the d valid channels of this head)
+      mbar_wait(od, (T - 1) & 1);
+      tc_fence_after();
+      if constexpr (Cfg::kSumTC) {
+        l_run = __uint_as_float(tmem_ld1(o_tmem + D));  // column D of O = sum_k P[:, k] (ones column of V)
+        tmem_ld_wait();
+      }
+    } else {
     if constexpr (QT == 2) {
       if (kPingPong && tq == 1) named_bar_arrive(1, 256);  // warpgroup 0 owns the exp unit first
     }
     // one KV tile of the online softmax; kMasked is only instantiated for the LAST tile (ragged nk), so the
     // 128-element mask (ISETP + SEL per element once if-converted) stays out of the steady-state loop
-    // S row of the current tile.  kSepP streams it: as soon as the exps of a 32-column chunk of tile j are done, the
-    // same registers receive that chunk of S(j+1) (tcgen05.ld is asynchronous), so the TMEM read and the wait for
-    // Q K_{j+1}^T leave the per-tile critical path.
     uint32_t sv[4][32];
-    if constexpr (Cfg::kSepP) {
-      mbar_wait(&s_full[tq], 0);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tmem_base + lane_base + tq * 128 + c * 32, sv[c]);
-    }
     auto softmax_tile = [&](const int j, auto masked_tag) {
       constexpr bool kMasked = decltype(masked_tag)::value;
       const int sb = (QT == 2) ? tq : (j & 1);                         // S / P buffer
       [[maybe_unused]] const uint32_t s_par = (QT == 2) ? (j & 1) : ((j >> 1) & 1);
       uint64_t* od = &o_done[(QT == 2) ? tq : 0];
       const uint32_t s_tmem = tmem_base + lane_base + sb * 128;
-      SG_TS(0);
-      if constexpr (!Cfg::kSepP) {
-        mbar_wait(&s_full[sb], s_par);
-        tc_fence_after();
-        SG_TS(1);
+      mbar_wait(&s_full[sb], s_par);
+      tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
-      }
+      for (int c = 0; c < 4; ++c) tmem_ld32(s_tmem + c * 32, sv[c]);
       tmem_ld_wait();
-      if constexpr (Cfg::kSepP) {
-        // S_t(j) is in registers: the tensor core may overwrite it with Q_t K_{j+1}^T
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[tq]);
-      }
-      SG_TS(2);
       if constexpr (kMasked) {
         const int valid = p.nk - j * 128;  // keys valid in this tile (>= 1)
 #pragma unroll
@@ -425,7 +604,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
           }
         }
       };
-      if constexpr (QT == 2 && !Cfg::kSepP) wait_and_rescale();  // already satisfied: QK_{j} was issued after PV_{j-1}
+      if constexpr (QT == 2) wait_and_rescale();  // already satisfied: QK_{j} was issued after PV_{j-1}
       float2 sum2[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
       const float2 nm2 = make_float2(-m_used, -m_used), sc2 = make_float2(p.scale_log2, p.scale_log2);
       if constexpr (QT == 2) {
@@ -433,9 +612,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
         // 4-lane/clk exp unit.  Left alone they fall into lockstep (both in the exp phase, then both idle
         // behind the MMA chain); with the exp phase made exclusive, one group's TMEM load / row max / P store
         // / wait for the tensor core overlaps the other group's exps.  Barrier 1 + t admits warpgroup t.
-        SG_TS(3);
         if (kPingPong) named_bar_sync(1 + tq, 256);
-        SG_TS(4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
@@ -449,26 +626,10 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
             sum2[(i >> 1) & 3] = fadd2(sum2[(i >> 1) & 3], make_float2(e0, e1));
             pk[i >> 1] = pack_bf16x2(e0, e1);
           }
-          if constexpr (Cfg::kSepP) {
-            // PV_{j-1} must have retired before P_j overwrites P_{j-1}; its ~500 clk hide behind the row max and
-            // the first chunk of exps
-            if (c == 0) wait_and_rescale();
-          }
-          tmem_st16((Cfg::kSepP ? (tmem_base + lane_base + Cfg::kColP + tq * 64) : s_tmem) + c * 16, pk);
+          tmem_st16(s_tmem + c * 16, pk);
           // admit the other warpgroup (its tile j if we are group 0, tile j+1 if we are group 1)
           if (kPingPong && c == kHandoff && !(tq == 1 && j == T - 1)) named_bar_arrive(2 - tq, 256);
-          if constexpr (Cfg::kSepP) {
-            if (j + 1 < T) {
-              if (c == 0) {
-                mbar_wait(&s_full[tq], (j + 1) & 1);
-                tc_fence_after();
-                SG_TS(1);
-              }
-              tmem_ld32(s_tmem + c * 32, sv[c]);  // S(j+1), chunk c -> the registers chunk c of S(j) just left
-            }
-          }
         }
-        SG_TS(5);
       } else if constexpr (SHORT) {
         // single KV tile: no previous PV to overlap, P (aliasing S, which is in registers) is stored chunk by chunk
 #pragma unroll
@@ -506,7 +667,6 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
-      SG_TS(6);
     };
     for (int j = 0; j + 1 < T; ++j) softmax_tile(j, std::false_type{});
     if (p.nk % 128 != 0) {
@@ -518,6 +678,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
     // final: O / l  -> global (only the d valid channels of this head)
     mbar_wait(&o_done[(QT == 2) ? tq : 0], (T - 1) & 1);
     tc_fence_after();
+    }
     const float inv_l = 1.0f / l_run;
     const int q = q0 + 128 * tq + r;
     bf16* orow = p.o + static_cast<long long>(img) * p.o_stride_n + static_cast<long long>(q) * p.o_stride_t +
@@ -559,13 +720,10 @@ static int launch_attn(const AttnKParams& kp, int nq, int heads, int lanes, cuda
   if constexpr (!DBG && D == 40 && QT == 2) {
     if (kp.dbg != nullptr) return launch_attn<D, QT, true>(kp, nq, heads, lanes, stream);  // bring-up timeline build
   }
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<D, QT, DBG, SHORT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_kernel<D, QT, DBG, SHORT>), Cfg::kSmemBytes,
+                                   &configured))
+    return rc;
   dim3 grid((nq + 128 * QT - 1) / (128 * QT), heads, lanes);
   attn_kernel<D, QT, DBG, SHORT><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();

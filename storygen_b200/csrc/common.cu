@@ -7,15 +7,37 @@ namespace sg {
 
 static std::atomic<int64_t> g_launches{0};
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs)
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[kMaxDevices];
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE property of a kernel: set it once per (kernel, device).
+// `done` is the kernel's bit mask of configured devices; the attribute call is idempotent, so two threads racing on
+// the first launch both set it and both succeed.
+int ensure_dynamic_smem(const void* kernel, int bytes, std::atomic<uint64_t>* done) {
+  const int dev = current_device();
+  const uint64_t bit = (dev >= 0 && dev < kMaxDevices) ? (1ull << dev) : 0;
+  if (bit != 0 && (done->load(std::memory_order_acquire) & bit)) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (bit != 0) done->fetch_or(bit, std::memory_order_release);
+  return 0;
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -6,13 +6,19 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/storygen_b200.h"
 #include "ptx.cuh"
 
 namespace sg {
 
-int num_sms();
+constexpr int kMaxDevices = 64;
+int current_device();
+int num_sms();  // of the current device
 void count_launch(int n = 1);
+// one-time (per kernel and device, thread-safe) opt-in to > 48 KB of dynamic shared memory; returns 0 or a cudaError
+int ensure_dynamic_smem(const void* kernel, int bytes, std::atomic<uint64_t>* done);
 
 // rank in [2,5]; dims/strides in elements of bf16 -> strides given in BYTES (rank-1 entries, dim0 is
 // contiguous). Returns 0 or an SG_ERR_* / cudaError code.

@@ -486,13 +486,10 @@ extern "C" int sg_small_linear(const float* x, int32_t n, int32_t k, const void*
   if (k % 8 || k > 1280) return SG_ERR_SHAPE;
   const int rows = n < kSlMaxRows ? n : kSlMaxRows;
   const size_t smem = static_cast<size_t>(rows) * k * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSlMaxRows * 1280 * static_cast<int>(sizeof(float)));
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> configured{0};
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(small_linear_kernel),
+                                   kSlMaxRows * 1280 * static_cast<int>(sizeof(float)), &configured))
+    return rc;
   int blocks = (m + 2 * kSlWarps - 1) / (2 * kSlWarps);
   if (blocks > num_sms()) blocks = num_sms();
   small_linear_kernel<<<blocks, kSlWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(

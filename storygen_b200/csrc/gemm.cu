@@ -163,13 +163,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 template <int BN, int MODE>
 static int launch_gemm_mode(const GemmKParams& kp, int num_tiles, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<BN, MODE>), Cfg::kSmemBytes, &configured)) return rc;
   int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   gemm_kernel<BN, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();

@@ -313,6 +313,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// one 32-bit column of this warp's 32 lanes
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -411,6 +417,21 @@ __device__ __forceinline__ float exp2_fma(float x) {
   p = fmaf(p, f, 0.69326097f);
   p = fmaf(p, f, 0.99992812f);
   return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+// Two 2^x at once on the FMA pipe (packed f32x2 arithmetic): same range reduction and cubic as exp2_fma; per pair
+// 2 FMNMX + 2 LEA on the ALU pipe and 6 packed FMA-pipe instructions, no MUFU.
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f), nmagic = make_float2(-12582912.f, -12582912.f);
+  const float2 t = fadd2(x, magic);
+  const float2 u = fadd2(t, nmagic);
+  const float2 f = ffma2(u, make_float2(-1.f, -1.f), x);
+  float2 p = ffma2(f, make_float2(0.05517147f, 0.05517147f), make_float2(0.2426109f, 0.2426109f));
+  p = ffma2(p, f, make_float2(0.69326097f, 0.69326097f));
+  p = ffma2(p, f, make_float2(0.99992812f, 0.99992812f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
 }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -206,7 +206,7 @@ void test_timeline() {
   std::vector<long long> h(12 * 16 * 8);
   CK(cudaMemcpy(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost));
   long long t0 = h[(4 * 16 + 2) * 8 + 0];
-  printf("[timeline] clocks relative to warp4 tile2 start; slots: 0=before s_full wait 1=S ready 2=S in regs 3=max done 4=exp unit granted 5=exps+Pstore issued 6=P published\n");
+  printf("[timeline] clocks relative to warp4 tile2 start; slots: 0=tile start 1=S(j+1) ready (after chunk 0) 4=exps start 5=all chunks issued 6=P published + next row max done\n");
   for (int w : {4, 8}) for (int j = 2; j < 8; ++j) {
     printf("[timeline] warp %2d tile %d:", w, j);
     for (int k = 0; k < 7; ++k) printf(" %7lld", h[(w * 16 + j) * 8 + k] - t0);

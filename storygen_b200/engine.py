@@ -47,7 +47,8 @@ class UNetEngine:
         if cfg.cross_attention_dim % 64:
             raise NotImplementedError("cross_attention_dim must be a multiple of 64")
         self._pack()
-        self._stats = None
+        self._stats = None      # workspace of the forward in flight
+        self._own_stats = None  # engine-owned workspace for direct unet(...) calls (never handed to a captured graph)
 
     # ------------------------------------------------------------------------------------------
     # weight packing
@@ -203,7 +204,8 @@ class UNetEngine:
         n, L, d = text.shape
         if out is None:
             out = self._new(n * L, self.n_kv2)
-        return ops.linear(text.view(n * L, d), self.w_kv2_all, out)
+        with torch.cuda.device(self.dev):
+            return ops.linear(text.view(n * L, d), self.w_kv2_all, out)
 
     def _transformer(self, p, x, n, h, w, text_kv, n_text_tokens, image, kv_map, n_kv_lanes):
         """x (n, h, w, c); text_kv (n * L, n_kv2) bf16 from project_text; image None or (n_kv, R*hw, c) bf16.
@@ -285,8 +287,14 @@ class UNetEngine:
     # forward
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def forward(self, sample, timestep, encoder_hidden_states, image_hidden_states=None, kv_map=None, text_kv=None):
-        """text_kv: optional result of project_text(encoder_hidden_states) (cached across steps by the pipeline)."""
+    def forward(self, sample, timestep, encoder_hidden_states, image_hidden_states=None, kv_map=None, text_kv=None,
+                stats=None):
+        """text_kv: optional result of project_text(encoder_hidden_states) (cached across steps by the pipeline);
+        stats: optional caller-owned GroupNorm workspace (ops.groupnorm_ws) — a captured CUDA graph must own its own."""
+        with torch.cuda.device(self.dev):  # every launcher enqueues on the current device's current stream
+            return self._forward(sample, timestep, encoder_hidden_states, image_hidden_states, kv_map, text_kv, stats)
+
+    def _forward(self, sample, timestep, encoder_hidden_states, image_hidden_states, kv_map, text_kv, stats):
         dev = self.dev
         n, _, h, w = sample.shape
         if (h % (1 << self.model.num_upsamplers)) or (w % (1 << self.model.num_upsamplers)):
@@ -314,8 +322,14 @@ class UNetEngine:
         if kv_map is not None:
             kv_map = kv_map.to(dev, torch.int32).contiguous()
         need = ops._lib.load().sg_groupnorm_ws_floats(n, self.groups)
-        if self._stats is None or self._stats.numel() < need:
-            self._stats = torch.empty(need, dtype=F32, device=dev)
+        if stats is not None:
+            if stats.numel() < need or stats.device != dev or stats.dtype != F32:
+                raise ValueError(f"stats workspace needs {need} fp32 elements on {dev}")
+            self._stats = stats
+        else:
+            if self._own_stats is None or self._own_stats.numel() < need:
+                self._own_stats = torch.empty(need, dtype=F32, device=dev)
+            self._stats = self._own_stats
 
         # time embedding: features -> linear_1 -> SiLU -> linear_2, then all 22 time_emb_proj at once
         boc0 = self.boc[0]

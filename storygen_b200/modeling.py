@@ -352,6 +352,8 @@ class UNet2DConditionModel(nn.Module):
         if class_labels is not None:
             raise NotImplementedError("class conditioning is not part of the StoryGen configuration")
         out, taps = self.engine().forward(sample, timestep, encoder_hidden_states, image_hidden_states)
+        if self.dtype in (torch.float16, torch.bfloat16):
+            out = out.to(self.dtype)  # the reference returns the sample in the weights' dtype (inference.py:72-74)
         if not return_dict:
             return (out, taps)
         return UNet2DConditionOutput(sample=out, img_dif_conditions=taps)

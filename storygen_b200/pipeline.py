@@ -86,6 +86,14 @@ class _DenoiseLoop:
         self.tab, self.tab_i = tab.to(dev), tab_i.to(dev)
         self.par = torch.empty(nf + 3 * B + 2, dtype=F32, device=dev)
         self.par_i = torch.empty(nf, dtype=torch.int32, device=dev)
+        # the reference indexes alphas_cumprod on the host and raises IndexError past the table (model/pipeline.py:420-424
+        # via DDIMScheduler.add_noise); the add_noise kernel reads acp[t] unchecked, so the bound is enforced here
+        if int(tab_i.max()) >= self.acp.numel() or int(tab_i.min()) < 0:
+            raise IndexError(f"feature-pass timestep {int(tab_i.max())} is out of range for {self.acp.numel()} training "
+                             f"timesteps (stage {stage!r} with {R} prior frames)")
+        # GroupNorm statistics workspace of THIS loop: the captured graph bakes its address in, so it must not be
+        # shared with (and re-allocated by) other callers of the same engine
+        self.stats = ops.groupnorm_ws(max(nf, 3 * B), self.eng.groups, dev)
         self.graph = None
         self.kernels_per_step = 0
         self.kernel_launches = 0
@@ -104,6 +112,10 @@ class _DenoiseLoop:
         self.m_text[0].copy_(text_uncond, **nb)
         self.m_text[1].copy_(text_uncond, **nb)
         self.m_text[2].copy_(text_cond, **nb)
+        with torch.cuda.device(self.latents.device):
+            self._project()
+
+    def _project(self):
         self.eng.project_text(self.f_text.view(self.nf, *self.f_text.shape[3:]), out=self.f_kv)
         self.eng.project_text(self.m_text.view(3 * self.B, *self.m_text.shape[2:]), out=self.m_kv)
         self.kernel_launches += 2
@@ -113,14 +125,18 @@ class _DenoiseLoop:
         lat_shape = self.latents.shape[1:]
         ops.add_noise(self.f_src.view(nf, *lat_shape), self.f_eps.view(nf, *lat_shape), self.acp, self.par_i, self.f_noisy)
         taps = self.eng.forward(self.f_noisy, self.par[:nf], self.f_text.view(nf, *self.f_text.shape[3:]), None,
-                                text_kv=self.f_kv)[1]
+                                text_kv=self.f_kv, stats=self.stats)[1]
         cond = {k: v.view(2 * B, -1, v.shape[-1]) for k, v in taps.items()}
         self.lat3.view(3, B, -1).copy_(self.latents.view(1, B, -1).expand(3, B, -1))
         eps3 = self.eng.forward(self.lat3, self.par[nf:nf + 3 * B], self.m_text.view(3 * B, *self.m_text.shape[2:]), cond,
-                                kv_map=self.kv_map, text_kv=self.m_kv)[0]
+                                kv_map=self.kv_map, text_kv=self.m_kv, stats=self.stats)[0]
         ops.cfg_ddim_step(eps3, self.latents, self.s_img, self.s_txt, self.par[nf + 3 * B:])
 
     def run(self, use_cuda_graph: bool = True, callback=None, callback_steps: int = 1):
+        with torch.cuda.device(self.latents.device):  # kernels launch on the CURRENT device's stream
+            return self._run(use_cuda_graph, callback, callback_steps)
+
+    def _run(self, use_cuda_graph, callback, callback_steps):
         from ._lib import launch_count
         for s, t in enumerate(self.timesteps):
             self.par.copy_(self.tab[s])
@@ -180,7 +196,9 @@ class StableDiffusionPipeline:
         if images.ndim == 3:
             images = images[None, ...]
         images = (images * 255).round().astype("uint8")
-        return [Image.fromarray(image) for image in images]
+        # model/pipeline.py:486-491: one LIST per image (the reference applies DiffusionPipeline.numpy_to_pil to each
+        # image separately), which is why inference.py:117-120 saves `image[0]`
+        return [[Image.fromarray(image)] for image in images]
 
     # ---- text / image conditioning (the steps either side of the hot path; caller's modules) -----
     def _encode_prompt(self, prompt, device, num_images_per_prompt, do_classifier_free_guidance, negative_prompt):

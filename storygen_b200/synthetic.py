@@ -42,6 +42,32 @@ def input_bytes(inputs) -> int:
     return n
 
 
+def seeded_init_(model: torch.nn.Module, seed: int = 0, gain: float = 1.0):
+    """Deterministic synthetic weights keyed by STATE-DICT NAME (CPU generator seeded by crc32 of the key), so any
+    implementation of the 798-key UNet — this package, the test oracle, the reference — gets bit-identical tensors
+    for the same seed regardless of construction order or device.  The benchmark uses it so that its output can be
+    checked against a stored fp32 reference (tests/golden/bench_steps_fp32.pt)."""
+    import zlib
+    sd = model.state_dict()
+    new = {}
+    for key in sorted(sd):
+        shape = tuple(sd[key].shape)
+        g = torch.Generator("cpu").manual_seed((seed * 1000003 + zlib.crc32(key.encode())) % (2 ** 31))
+        r = torch.randn(shape, generator=g, dtype=torch.float32)
+        if len(shape) >= 2:  # conv / linear weight: variance preserving
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            w = r * (gain / fan_in ** 0.5)
+        elif key.endswith("weight"):  # norm scale
+            w = 1.0 + 0.1 * r
+        else:  # bias / norm shift
+            w = 0.05 * r
+        new[key] = w
+    model.load_state_dict(new)
+    return model
+
+
 def random_init_(model: torch.nn.Module, seed: int = 0):
     """Variance-preserving random weights, generated on the model's device (the values are irrelevant
     for throughput; parity tests use oracle/weights.py instead)."""

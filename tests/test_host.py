@@ -132,3 +132,15 @@ def test_feature_timesteps_and_pipeline_surface():
     fsig = inspect.signature(UNet2DConditionModel.forward)
     assert list(fsig.parameters)[1:] == ["sample", "timestep", "encoder_hidden_states", "image_hidden_states",
                                          "class_labels", "cross_attention_kwargs", "return_dict"]
+
+
+def test_numpy_to_pil_returns_one_list_per_image():
+    """model/pipeline.py:486-491: `.images` is a list of per-image lists; inference.py:117-120 saves `image[0]`."""
+    import numpy as np
+
+    from storygen_b200 import StableDiffusionPipeline
+    imgs = StableDiffusionPipeline.numpy_to_pil(np.random.rand(3, 16, 16, 3).astype("float32"))
+    assert isinstance(imgs, list) and len(imgs) == 3
+    assert all(isinstance(i, list) and len(i) == 1 and i[0].size == (16, 16) for i in imgs)
+    one = StableDiffusionPipeline.numpy_to_pil(np.random.rand(16, 16, 3).astype("float32"))
+    assert len(one) == 1 and one[0][0].mode == "RGB"
