@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 7
+#define SG_ABI_VERSION 8
 
 #define SG_ERR_SHAPE (-1)   /* unsupported / inconsistent shape            */
 #define SG_ERR_ALIGN (-2)   /* pointer or stride not 16-byte aligned        */
@@ -99,9 +99,27 @@ typedef struct sg_gemm_args {
   void* out; /* bf16 [M, ldo] */
   int64_t ldo;
   int64_t* debug_timeline; /* bring-up aid: device int64[10*8*8] phase clocks of CTA 0, or NULL */
+  /* ---- fused normalisation hooks (all optional) ----------------------------------------------
+   * LayerNorm is folded INTO the GEMMs either side of it (model/attention.py:250,268,283,298 `norm1..norm4` followed by
+   * to_q / to_k / to_v / ff.net[0]):   LN(x) W^T + b = rstd_m (x W'^T - mean_m csum) + b',
+   *   W' = W diag(gamma) (bf16),  csum[n] = sum_k W'[n,k],  b' = b + W beta   (packed once per model),
+   * so the normalised activation is never written: the PRODUCER of x emits per-row partial (sum, sum of squares) of its
+   * output (`row_stats_out`), the CONSUMER multiplies the raw x and applies mean / rstd per row in its epilogue.
+   * GroupNorm statistics likewise come from the producer: `col_stats_out` receives per-channel partial sums of
+   * 32-row blocks, reduced to (mean, rstd) per (image, group) by sg_groupnorm_finalize. */
+  float* row_stats_out;  /* fp32 [sg_gemm_row_stat_parts(args)][M][2]: (sum, sumsq) of output row m over the columns of
+                            one (N tile, epilogue warpgroup); modes LINEAR only */
+  const float* ln_stats; /* fp32 [ln_parts][M][2]: row partials of the A operand (M = this GEMM's rows) or NULL */
+  const float* ln_csum;  /* fp32 [N] column sums of W' (required with ln_stats)                                */
+  int32_t ln_parts;
+  float ln_eps;
+  float* col_stats_out;  /* fp32 [M tiles * 4][N][2]: per (128-row tile, 32-row quarter, output channel) partial
+                            (sum, sumsq) over the quarter's valid rows; modes LINEAR only                       */
 } sg_gemm_args;
 
 int sg_gemm(const sg_gemm_args* args, void* stream);
+/* number of row-statistics partials sg_gemm(args) writes per row (2 x its N tiles; depends on N and the tile grid) */
+int sg_gemm_row_stat_parts(const sg_gemm_args* args);
 
 /* ---- fused attention core (FlashAttention-style, tcgen05 + TMEM) -----------------------------
  * o[n, q, h*d:(h+1)*d] = softmax(scale * Q_h K_h^T) V_h for every (n, h); Q/K/V are read in place
@@ -147,6 +165,23 @@ int sg_groupnorm_stats(const void* x0, int32_t c0, const void* x1, int32_t c1, i
 int sg_groupnorm_apply(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img,
                        int32_t hw, int32_t groups, float eps, const float* stats, const float* gamma,
                        const float* beta, int32_t silu, void* y, void* stream);
+
+/* GroupNorm from producer-side statistics (no separate pass over the activations).
+ * sg_groupnorm_finalize: reduces the col_stats_out partials of up to two producing GEMMs (the channel-concat x0 | x1
+ * of the skip connections, model/unet_2d_blocks.py:609,626,716) to mean_rstd[n_img][groups][2], in a fixed order
+ * (deterministic), accumulating in fp64 so that E[x^2] - mean^2 does not cancel for channels with |mean| >> std.
+ * parts_i: the col_stats_out buffer of source i, [(M tiles) * 4][c_i][2].  Both sources were produced on the same
+ * output pixel grid, tiled in boxes of bw x bh x bn pixels (bw * bh * bn == 128): image n owns the tiles
+ * [ (n / bn) * tiles_xy, (n / bn + 1) * tiles_xy ) and, inside each, the 4 / bn quarters starting at (n % bn) * (4 / bn);
+ * pass tiles_xy = (tiles along x) * (tiles along y) and imgs_per_tile = bn (1, 2 or 4: a 32-row quarter never spans
+ * two images, i.e. hw >= 32).
+ * sg_groupnorm_apply_ms: y = [SiLU]((x - mean) * rstd * gamma + beta) with those statistics. */
+int sg_groupnorm_finalize(const float* parts0, int32_t c0, const float* parts1, int32_t c1, int32_t n_img, int32_t hw,
+                          int32_t tiles_xy, int32_t imgs_per_tile, int32_t groups, float eps, float* mean_rstd,
+                          void* stream);
+int sg_groupnorm_apply_ms(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img, int32_t hw,
+                          int32_t groups, const float* mean_rstd, const float* gamma, const float* beta,
+                          int32_t silu, void* y, void* stream);
 
 /* LayerNorm over the channel dim of a (rows, c) bf16 tensor; up to two affine outputs from one
  * statistics pass (norm2 and norm4 read the same tensor, model/attention.py:268,283). */

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # STORYGEN_B200_LIB: developer override for A/B runs of an alternative in-tree build of the same library
 LIB_PATH = os.environ.get("STORYGEN_B200_LIB") or os.path.join(_HERE, "libstorygen_b200.so")
 
-SG_ABI_VERSION = 7
+SG_ABI_VERSION = 8
 SG_MAX_SRC = 4
 SG_MAX_SEGS = 24
 SG_EPI_LINEAR = 0
@@ -23,7 +23,7 @@ EXPORTS = [
     "sg_abi_version", "sg_sizeof_gemm_args", "sg_sizeof_attn_args", "sg_launch_count", "sg_error_string",
     "sg_gemm", "sg_attention", "sg_groupnorm_ws_floats", "sg_groupnorm_stats", "sg_groupnorm_apply",
     "sg_layernorm", "sg_timestep_features", "sg_small_linear", "sg_upsample2x", "sg_im2col3x3_nchw",
-    "sg_add_noise", "sg_cfg_ddim_step",
+    "sg_add_noise", "sg_cfg_ddim_step", "sg_gemm_row_stat_parts", "sg_groupnorm_finalize", "sg_groupnorm_apply_ms",
 ]
 
 
@@ -42,7 +42,9 @@ class SgGemmArgs(C.Structure):
                 ("bw", C.c_int32), ("bh", C.c_int32), ("bn", C.c_int32), ("b", C.c_void_p), ("N", C.c_int64),
                 ("Ktot", C.c_int64), ("mode", C.c_int32), ("out_channels", C.c_int32), ("res_scale", C.c_float), ("bias", C.c_void_p),
                 ("lane_bias", C.c_void_p), ("ld_lane_bias", C.c_int64), ("residual", C.c_void_p),
-                ("ldr", C.c_int64), ("out", C.c_void_p), ("ldo", C.c_int64), ("debug_timeline", C.c_void_p)]
+                ("ldr", C.c_int64), ("out", C.c_void_p), ("ldo", C.c_int64), ("debug_timeline", C.c_void_p),
+                ("row_stats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_csum", C.c_void_p),
+                ("ln_parts", C.c_int32), ("ln_eps", C.c_float), ("col_stats_out", C.c_void_p)]
 
 
 class SgAttnArgs(C.Structure):
@@ -84,10 +86,13 @@ def load():
         raise LibraryError("argument struct size mismatch between the library and the ctypes mirror")
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     lib.sg_gemm.argtypes = [C.POINTER(SgGemmArgs), vp]
+    lib.sg_gemm_row_stat_parts.argtypes = [C.POINTER(SgGemmArgs)]
     lib.sg_attention.argtypes = [C.POINTER(SgAttnArgs), vp]
     lib.sg_groupnorm_ws_floats.argtypes = [i32, i32]
     lib.sg_groupnorm_stats.argtypes = [vp, i32, vp, i32, i32, i32, i32, f32, vp, vp]
     lib.sg_groupnorm_apply.argtypes = [vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, vp, i32, vp, vp]
+    lib.sg_groupnorm_finalize.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp]
+    lib.sg_groupnorm_apply_ms.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]
     lib.sg_layernorm.argtypes = [vp, i64, i32, f32, vp, vp, vp, vp, vp, vp, vp]
     lib.sg_timestep_features.argtypes = [vp, i32, i32, vp, vp]
     lib.sg_small_linear.argtypes = [vp, i32, i32, vp, vp, i32, i32, i32, vp, vp]

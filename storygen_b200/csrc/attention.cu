@@ -51,6 +51,12 @@ constexpr bool kPingPong2 = SG_ATTN2_PINGPONG != 0;
 #endif
 // bit (i % 8) set: pair i of a 32-column chunk takes both exps on the FMA pipe (0x11 = 1 in 4, 0x49 = 3 in 8, 0x55 = 1 in 2)
 constexpr unsigned kPolyMask2 = SG_ATTN2_POLY_MASK;
+#ifndef SG_ATTN2_PDEFER
+#define SG_ATTN2_PDEFER 1
+#endif
+// 1: chunk 0 of P_j stays in registers until the exps of chunk 1 are done, so the wait for P V_{j-1} (which guards the
+// single P buffer and the O rescale) moves half a chunk later and stops stalling the exp stream
+constexpr bool kPDefer2 = SG_ATTN2_PDEFER != 0;
 constexpr int kPolyEvery = SG_ATTN_POLY_EVERY;  // 0 = all exps on MUFU; 4 = 1 in 4 on the FMA pipe; 2 = 1 in 2  // the other warpgroup may start its exps once chunk kHandoff (of 4) is issued
 
 struct AttnKParams {
@@ -451,6 +457,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
         max_reset();
         if (kPingPong2) named_bar_sync(1 + tq, 256);
         SG_TS(4);
+        [[maybe_unused]] uint32_t pk0[16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
@@ -475,9 +482,9 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
             if constexpr (!Cfg::kSumTC) sum2[(i >> 1) & 3] = fadd2(sum2[(i >> 1) & 3], e);
             pk[i >> 1] = pack_bf16x2(e.x, e.y);
           }
-          if (c == 0 && j > 0) {
+          if (c == (kPDefer2 ? 1 : 0) && j > 0) {
             // P V_{j-1} must have retired before P_j overwrites P_{j-1} and before the O row may be rescaled; its
-            // ~500 clk hide behind the first chunk of exps.  o_done phases are consumed strictly in order.
+            // ~500 clk hide behind the first chunk(s) of exps.  o_done phases are consumed strictly in order.
             mbar_wait(od, (j - 1) & 1);
             tc_fence_after();
             if (__any_sync(0xffffffffu, need)) {
@@ -492,7 +499,17 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
               }
             }
           }
-          tmem_st16(p_tmem + c * 16, pk);
+          if constexpr (kPDefer2) {
+            if (c == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pk0[i] = pk[i];
+            } else {
+              if (c == 1) tmem_st16(p_tmem, pk0);
+              tmem_st16(p_tmem + c * 16, pk);
+            }
+          } else {
+            tmem_st16(p_tmem + c * 16, pk);
+          }
           if (kPingPong2 && c == kHandoff && !(tq == 1 && j == T - 1)) named_bar_arrive(2 - tq, 256);
           if constexpr (kHasNext) {
             if (c == 0) {

@@ -177,6 +177,103 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x0, int c0, const bf16*
   }
 }
 
+// GroupNorm statistics from the PRODUCER's epilogue (sg_gemm col_stats_out): reduce the per-(32-row quarter, channel)
+// partials of image n / group g to (mean, rstd).  One block per (group, image); every thread sums a fixed subset in a
+// fixed order and the block tree is fixed, so the result is deterministic; fp64 accumulation keeps E[x^2] - mean^2
+// from cancelling when |mean| >> std.
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float2* __restrict__ parts0, int c0,
+                                                          const float2* __restrict__ parts1, int c1, int hw,
+                                                          int tiles_xy, int bn, int groups, float eps,
+                                                          float2* __restrict__ mean_rstd) {
+  __shared__ double s_s[128], s_q[128];
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int C = c0 + c1, cpg = C / groups;
+  const int nq = 4 / bn, q0 = (n % bn) * nq;
+  const long long tile0 = static_cast<long long>(n / bn) * tiles_xy;
+  const int items = tiles_xy * nq * cpg;
+  double s = 0.0, q = 0.0;
+  for (int it = threadIdx.x; it < items; it += 128) {
+    const int ch = g * cpg + it % cpg;
+    const int bi = it / cpg;
+    const long long blk = (tile0 + bi / nq) * 4 + q0 + bi % nq;
+    const float2 e = (ch < c0) ? __ldg(parts0 + blk * c0 + ch) : __ldg(parts1 + blk * c1 + (ch - c0));
+    s += static_cast<double>(e.x);
+    q += static_cast<double>(e.y);
+  }
+  s_s[threadIdx.x] = s;
+  s_q[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_s[threadIdx.x] += s_s[threadIdx.x + o];
+      s_q[threadIdx.x] += s_q[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double cnt = static_cast<double>(hw) * cpg;
+    const double mean = s_s[0] / cnt;
+    double var = s_q[0] / cnt - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    mean_rstd[static_cast<long long>(n) * groups + g] =
+        make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
+  }
+}
+
+// y = [SiLU]((x - mean) * rstd * gamma + beta) with per-(image, group) statistics computed elsewhere
+__global__ void gn_apply_ms_kernel(const bf16* __restrict__ x0, int c0, const bf16* __restrict__ x1, int c1, int hw,
+                                   int groups, const float2* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int silu, bf16* __restrict__ y) {
+  const int C = c0 + c1, V = C / 8, PS = blockDim.x / V;
+  const int v = threadIdx.x % V, pl = threadIdx.x / V;
+  const int n = blockIdx.y;
+  const int cpg = C / groups;
+  const int slabs = gridDim.x, slab = blockIdx.x;
+  const int p_begin = static_cast<int>(static_cast<long long>(hw) * slab / slabs);
+  const int p_end = static_cast<int>(static_cast<long long>(hw) * (slab + 1) / slabs);
+  const bool from0 = (v * 8 < c0);
+  const bf16* base = from0 ? x0 + static_cast<long long>(n) * hw * c0 + v * 8
+                           : x1 + static_cast<long long>(n) * hw * c1 + (v * 8 - c0);
+  const int cs = from0 ? c0 : c1;
+  // first loads in flight before the (dependent) statistics / affine parameters are fetched
+  uint4 raw[4];
+  const int p0 = p_begin + pl;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (p0 + u * PS < p_end) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p0 + u * PS) * cs));
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = v * 8 + i;
+    const float2 mr = __ldg(mean_rstd + static_cast<long long>(n) * groups + c / cpg);
+    const float ga = __ldg(gamma + c) * mr.y;
+    a[i] = ga;
+    b[i] = __ldg(beta + c) - mr.x * ga;
+  }
+  bf16* ybase = y + static_cast<long long>(n) * hw * C + v * 8;
+  for (int p = p0; p < p_end; p += 4 * PS) {
+    uint4 nxt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (p + (4 + u) * PS < p_end)
+        nxt[u] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p + (4 + u) * PS) * cs));
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (p + u * PS < p_end) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float t = fmaf(f[i], a[i], b[i]);
+          f[i] = silu ? silu_f(t) : t;
+        }
+        *reinterpret_cast<uint4*>(ybase + static_cast<long long>(p + u * PS) * C) = pack8(f);
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) raw[u] = nxt[u];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row held in registers (C <= 1280), two affine outputs
 // ------------------------------------------------------------------------------------------------
@@ -448,6 +545,35 @@ extern "C" int sg_groupnorm_apply(const void* x0, int32_t c0, const void* x1, in
   gn_apply_kernel<<<dim3(chunks, n_img), V * PS, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const bf16*>(x0), c0, static_cast<const bf16*>(x1), c1, hw, groups, chunks, eps, stats, gamma,
       beta, silu, static_cast<bf16*>(y));
+  SG_LAUNCH_END();
+}
+
+extern "C" int sg_groupnorm_finalize(const float* parts0, int32_t c0, const float* parts1, int32_t c1, int32_t n_img,
+                                     int32_t hw, int32_t tiles_xy, int32_t imgs_per_tile, int32_t groups, float eps,
+                                     float* mean_rstd, void* stream) {
+  const int C = c0 + c1;
+  if (!parts0 || !mean_rstd || (c1 > 0 && !parts1)) return SG_ERR_ARG;
+  if (C % groups || groups < 1 || tiles_xy < 1 || n_img < 1) return SG_ERR_SHAPE;
+  if (imgs_per_tile != 1 && imgs_per_tile != 2 && imgs_per_tile != 4) return SG_ERR_SHAPE;
+  if (static_cast<long long>(tiles_xy) * 128 / imgs_per_tile < hw) return SG_ERR_SHAPE;  // the quarters must cover the image
+  gn_finalize_kernel<<<dim3(groups, n_img), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(parts0), c0, reinterpret_cast<const float2*>(parts1), c1, hw, tiles_xy,
+      imgs_per_tile, groups, eps, reinterpret_cast<float2*>(mean_rstd));
+  SG_LAUNCH_END();
+}
+
+extern "C" int sg_groupnorm_apply_ms(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img,
+                                     int32_t hw, int32_t groups, const float* mean_rstd, const float* gamma,
+                                     const float* beta, int32_t silu, void* y, void* stream) {
+  const int C = c0 + c1;
+  if (!x0 || !mean_rstd || !gamma || !beta || !y || (c1 > 0 && !x1)) return SG_ERR_ARG;
+  if (C % 8 || c0 % 8 || C % groups || groups > 64 || C / 8 > 1024) return SG_ERR_SHAPE;
+  int V, PS;
+  gn_block_shape(C, &V, &PS);
+  const int chunks = gn_chunks(hw, n_img, PS);
+  gn_apply_ms_kernel<<<dim3(chunks, n_img), V * PS, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x0), c0, static_cast<const bf16*>(x1), c1, hw, groups,
+      reinterpret_cast<const float2*>(mean_rstd), gamma, beta, silu, static_cast<bf16*>(y));
   SG_LAUNCH_END();
 }
 

@@ -182,9 +182,27 @@ static int launch_gemm(const GemmKParams& kp, int num_tiles, cudaStream_t stream
   }
 }
 
+// N tile width: the main loop is bound by the bytes an SM must pull into shared memory per MMA (A 16 KB + B 128 B x BN
+// per k-block, ~80-100 B/clk/SM achievable: profiles/r01_ubench_tma_ingest.log), so wide tiles win: 256 with a
+// ragged last tile from N = 512 on.  Small problems (deep UNet levels: M = 768 / 1536 rows) are the exception: when
+// the tile count would leave more than half of the SMs idle, halve the tile width until the grid fills them.
+static int pick_bn_tile(const sg_gemm_args* a) {
+  int bn_tile = (a->N % 256 == 0 || a->N >= 512) ? 256 : ((a->N % 160 == 0) ? 160 : ((a->N % 128 == 0) ? 128 : 64));
+  const long long m_tiles = static_cast<long long>((a->out_w + a->bw - 1) / a->bw) * ((a->out_h + a->bh - 1) / a->bh) *
+                            ((a->out_n + a->bn - 1) / a->bn);
+  while (bn_tile > 64 && bn_tile % 128 == 0 && m_tiles * ((a->N + bn_tile - 1) / bn_tile) * 2 <= num_sms()) bn_tile /= 2;
+  return bn_tile;
+}
+
 }  // namespace sg
 
 using namespace sg;
+
+extern "C" int sg_gemm_row_stat_parts(const sg_gemm_args* a) {
+  if (a == nullptr || a->bw < 1 || a->bh < 1 || a->bn < 1 || a->N < 1) return SG_ERR_ARG;
+  const int bn_tile = pick_bn_tile(a);
+  return 2 * static_cast<int>((a->N + bn_tile - 1) / bn_tile);
+}
 
 extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   if (a == nullptr || a->b == nullptr || a->out == nullptr) return SG_ERR_ARG;
@@ -194,6 +212,11 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   if (a->N % 32 != 0 || a->Ktot % kBK != 0) return SG_ERR_SHAPE;
   if (a->mode != SG_EPI_LINEAR && a->mode != SG_EPI_GEGLU && a->mode != SG_EPI_NCHW_F32) return SG_ERR_ARG;
   if (a->mode == SG_EPI_NCHW_F32 && (a->out_channels < 1 || a->out_channels > 32 || a->N != 32)) return SG_ERR_SHAPE;
+  if ((a->row_stats_out || a->col_stats_out) && a->mode != SG_EPI_LINEAR) return SG_ERR_ARG;
+  if (a->ln_stats && (!a->ln_csum || a->ln_parts < 1 || a->mode == SG_EPI_NCHW_F32)) return SG_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(a->row_stats_out) & 7) || (reinterpret_cast<uintptr_t>(a->col_stats_out) & 15) ||
+      (reinterpret_cast<uintptr_t>(a->ln_stats) & 7))
+    return SG_ERR_ALIGN;
   if ((reinterpret_cast<uintptr_t>(a->out) & 15) || (a->mode != SG_EPI_NCHW_F32 && (a->ldo % 8)) ||
       (a->residual && ((reinterpret_cast<uintptr_t>(a->residual) & 15) || (a->ldr % 8))))
     return SG_ERR_ALIGN;
@@ -222,17 +245,7 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
     if (rc != 0) return rc;
   }
 
-  // tile width: the main loop is bound by the bytes an SM must pull into shared memory per MMA (A 16 KB + B 128 B x BN
-  // per k-block, ~80-100 B/clk/SM achievable: profiles/r01_ubench_tma_ingest.log), so wide tiles win: 256 with a
-  // ragged last tile from N = 512 on.  Small problems (deep UNet levels: M = 768 / 1536 rows) are the exception: when
-  // the tile count would leave more than half of the SMs idle, halve the tile width until the grid fills them.
-  int bn_tile = (a->N % 256 == 0 || a->N >= 512) ? 256 : ((a->N % 160 == 0) ? 160 : ((a->N % 128 == 0) ? 128 : 64));
-  {
-    const long long m_tiles = static_cast<long long>((a->out_w + a->bw - 1) / a->bw) * ((a->out_h + a->bh - 1) / a->bh) *
-                              ((a->out_n + a->bn - 1) / a->bn);
-    while (bn_tile > 64 && bn_tile % 128 == 0 && m_tiles * ((a->N + bn_tile - 1) / bn_tile) * 2 <= num_sms())
-      bn_tile /= 2;
-  }
+  const int bn_tile = pick_bn_tile(a);
   {
     uint64_t dims[2] = {static_cast<uint64_t>(a->Ktot), static_cast<uint64_t>(a->N)};
     uint64_t strides[1] = {static_cast<uint64_t>(a->Ktot) * 2};
@@ -268,6 +281,14 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   kp.out = static_cast<bf16*>(a->out);
   kp.ldo = a->ldo;
   kp.dbg = reinterpret_cast<long long*>(a->debug_timeline);
+  kp.M = static_cast<long long>(a->out_w) * a->out_h * a->out_n;
+  kp.row_stats_out = a->row_stats_out;
+  kp.ln_stats = a->ln_stats;
+  kp.ln_csum = a->ln_csum;
+  kp.ln_parts = a->ln_parts;
+  kp.ln_inv_k = 1.0f / static_cast<float>(a->Ktot);
+  kp.ln_eps = a->ln_eps;
+  kp.col_stats_out = a->col_stats_out;
 
   const int num_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n * kp.num_n_tiles;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);

@@ -35,6 +35,14 @@ struct GemmKParams {
   bf16* out;
   long long ldo;
   long long* dbg;  // bring-up aid: phase clocks of CTA 0 (NULL in production)
+  // fused normalisation hooks (include/storygen_b200.h): all optional
+  long long M;            // total output rows (stride of the row-statistics parts)
+  float* row_stats_out;   // [2 * num_n_tiles][M][2]
+  const float* ln_stats;  // [ln_parts][M][2]
+  const float* ln_csum;   // [N]
+  int ln_parts;
+  float ln_inv_k, ln_eps;
+  float* col_stats_out;   // [num_m_tiles * 4][N][2]
 };
 
 template <int BN>
@@ -44,7 +52,7 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kWarpScratch = 2048 + 128;  // per epilogue warp: [32 rows x 64 B] transpose buffer + 32 bias floats
+  static constexpr int kWarpScratch = 2048 + 256;  // per epilogue warp: [32 rows x 64 B] transpose buffer + 32 bias + 32 csum floats
   static constexpr int kScratchBytes = kEpiWarps * kWarpScratch;
   static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align*/ + 128 /*barriers*/;
   static_assert(kSmemBytes <= 231424, "exceeds the 227 KB - 1 KB (reserved) dynamic shared memory limit");
@@ -67,6 +75,22 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-0.70710678f * z, e, fmaxf(x, 0.f));  // 0.5 |x| = z / sqrt(2)
 }
 
+
+// Column sums over the 32 lanes of a warp of v[0..31] (lane = row, index = column): after the 5 exchange levels lane L
+// holds the total of column L in v[0].  31 shuffles instead of 5 x 32.
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], const int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
 
 // One output tile of the epilogue, executed by one epilogue warp (quarter = TMEM lane quarter it may access,
 // grp = epilogue warpgroup 0/1 taking the 32-column chunks c = grp, grp+2, ...).  t_row = TMEM address of this
@@ -154,6 +178,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
 
   float bias_pre = 0.f;
   if (p.bias != nullptr && grp < kChunks && nt * BN + grp * 32 < p.N) bias_pre = __ldg(p.bias + nt * BN + grp * 32 + lane);
+  // fused LayerNorm of the A operand: mean / rstd of this thread's row from the producer's row partials
+  const bool use_ln = (p.ln_stats != nullptr);  // kernel-uniform
+  const uint32_t csum_u32 = scratch_u32 + 2048 + 128;
+  float ln_mean = 0.f, ln_rstd = 1.f, csum_pre = 0.f;
+  if (use_ln) {
+    if (row_ok) {
+      const long long m = (static_cast<long long>(n) * p.out_h + y) * p.out_w + x;
+      float s = 0.f, q = 0.f;
+      for (int pp = 0; pp < p.ln_parts; ++pp) {
+        const float2 e = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(pp) * p.M + m);
+        s += e.x;
+        q += e.y;
+      }
+      ln_mean = s * p.ln_inv_k;
+      ln_rstd = rsqrtf(fmaxf(q * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
+    }
+    if (grp < kChunks && nt * BN + grp * 32 < p.N) csum_pre = __ldg(p.ln_csum + nt * BN + grp * 32 + lane);
+  }
+  // statistics of the OUTPUT for the consumers' LayerNorm (per row) / GroupNorm (per channel): LINEAR mode only
+  const bool row_out = (MODE == SG_EPI_LINEAR) && (p.row_stats_out != nullptr);
+  const bool col_out = (MODE == SG_EPI_LINEAR) && (p.col_stats_out != nullptr);
+  float rs_acc[4] = {0.f, 0.f, 0.f, 0.f}, rq_acc[4] = {0.f, 0.f, 0.f, 0.f};  // direct path uses [0]
   SG_GT(1);
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
@@ -176,6 +222,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[kDouble ? (ci & 1) : 0][j]);
+        if (use_ln) {
+          // LN(x) W^T = rstd (x W'^T - mean csum): acc holds x W'^T
+          sts32(csum_u32 + lane * 4, __float_as_uint(csum_pre));
+          if (ci + 1 < kMine && c + 2 < kChunks && col0 + 64 < p.N) csum_pre = __ldg(p.ln_csum + col0 + 64 + lane);
+          __syncwarp();
+          const float nm = -ln_mean;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 cc = lds128(csum_u32 + j * 16);
+            f[4 * j + 0] = ln_rstd * fmaf(nm, __uint_as_float(cc.x), f[4 * j + 0]);
+            f[4 * j + 1] = ln_rstd * fmaf(nm, __uint_as_float(cc.y), f[4 * j + 1]);
+            f[4 * j + 2] = ln_rstd * fmaf(nm, __uint_as_float(cc.z), f[4 * j + 2]);
+            f[4 * j + 3] = ln_rstd * fmaf(nm, __uint_as_float(cc.w), f[4 * j + 3]);
+          }
+          __syncwarp();  // every lane has read the vector before the next chunk overwrites it
+        }
         if (p.bias != nullptr) {
           sts32(bias_u32 + lane * 4, __float_as_uint(bias_pre));
           if (ci + 1 < kMine && c + 2 < kChunks && col0 + 64 < p.N) bias_pre = __ldg(p.bias + col0 + 64 + lane);
@@ -188,6 +250,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
             f[4 * j + 2] += __uint_as_float(bb.z);
             f[4 * j + 3] += __uint_as_float(bb.w);
           }
+          __syncwarp();  // every lane has read the vector before the next chunk overwrites it
         }
         if (lane_bias_row != nullptr && row_ok) {
           const float4* b4 = reinterpret_cast<const float4*>(lane_bias_row + col0);
@@ -214,27 +277,54 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
         } else if (MODE == SG_EPI_LINEAR && !tr) {
           // direct path (large K: the epilogue is hidden behind the main loop and extra smem traffic would
           // steal operand bandwidth from the tensor core): own row, 4 x 16-byte stores
-          if (row_ok) {
-            const long long m = (static_cast<long long>(n) * p.out_h + y) * p.out_w + x;
-            uint4* o4 = reinterpret_cast<uint4*>(p.out + m * p.ldo + col0);
+          // (acc + bias) is rounded to bf16 before the residual add (as the reference's separate ops do); the
+          // statistics are taken from the fp32 value just before the final rounding
+          float fin[32];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 q;
-              q.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              if (use_res) {
-                const uint4 rq = res[ci][j];
-                float2 a0 = unpack_bf16x2(q.x), a1 = unpack_bf16x2(q.y), a2 = unpack_bf16x2(q.z), a3 = unpack_bf16x2(q.w);
-                float2 r0 = unpack_bf16x2(rq.x), r1 = unpack_bf16x2(rq.y), r2 = unpack_bf16x2(rq.z), r3 = unpack_bf16x2(rq.w);
-                q.x = pack_bf16x2(fmaf(p.res_scale, r0.x, a0.x), fmaf(p.res_scale, r0.y, a0.y));
-                q.y = pack_bf16x2(fmaf(p.res_scale, r1.x, a1.x), fmaf(p.res_scale, r1.y, a1.y));
-                q.z = pack_bf16x2(fmaf(p.res_scale, r2.x, a2.x), fmaf(p.res_scale, r2.y, a2.y));
-                q.w = pack_bf16x2(fmaf(p.res_scale, r3.x, a3.x), fmaf(p.res_scale, r3.y, a3.y));
-              }
-              o4[j] = q;
+          for (int j = 0; j < 4; ++j) {
+            uint4 q;
+            q.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+            q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+            q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            float2 a0 = unpack_bf16x2(q.x), a1 = unpack_bf16x2(q.y), a2 = unpack_bf16x2(q.z), a3 = unpack_bf16x2(q.w);
+            if (use_res) {
+              const uint4 rq = res[ci][j];
+              float2 r0 = unpack_bf16x2(rq.x), r1 = unpack_bf16x2(rq.y), r2 = unpack_bf16x2(rq.z), r3 = unpack_bf16x2(rq.w);
+              a0.x = fmaf(p.res_scale, r0.x, a0.x); a0.y = fmaf(p.res_scale, r0.y, a0.y);
+              a1.x = fmaf(p.res_scale, r1.x, a1.x); a1.y = fmaf(p.res_scale, r1.y, a1.y);
+              a2.x = fmaf(p.res_scale, r2.x, a2.x); a2.y = fmaf(p.res_scale, r2.y, a2.y);
+              a3.x = fmaf(p.res_scale, r3.x, a3.x); a3.y = fmaf(p.res_scale, r3.y, a3.y);
+              q.x = pack_bf16x2(a0.x, a0.y);
+              q.y = pack_bf16x2(a1.x, a1.y);
+              q.z = pack_bf16x2(a2.x, a2.y);
+              q.w = pack_bf16x2(a3.x, a3.y);
             }
+            fin[8 * j + 0] = a0.x; fin[8 * j + 1] = a0.y; fin[8 * j + 2] = a1.x; fin[8 * j + 3] = a1.y;
+            fin[8 * j + 4] = a2.x; fin[8 * j + 5] = a2.y; fin[8 * j + 6] = a3.x; fin[8 * j + 7] = a3.y;
+            if (row_ok) {
+              const long long m = (static_cast<long long>(n) * p.out_h + y) * p.out_w + x;
+              reinterpret_cast<uint4*>(p.out + m * p.ldo + col0)[j] = q;
+            }
+          }
+          if (row_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              rs_acc[0] += fin[j];
+              rq_acc[0] = fmaf(fin[j], fin[j], rq_acc[0]);
+            }
+          }
+          if (col_out) {
+            // per-channel (sum, sumsq) over this warp's 32 rows (rows outside the image contribute zero)
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              fin[j] = row_ok ? fin[j] : 0.f;
+              sq[j] = fin[j] * fin[j];
+            }
+            const float cs = warp_column_sums(fin, lane), cq = warp_column_sums(sq, lane);
+            reinterpret_cast<float2*>(p.col_stats_out)[(static_cast<long long>(mt) * 4 + quarter) * p.N + col0 + lane] =
+                make_float2(cs, cq);
           }
         } else {
           const int buf = 0;
@@ -267,26 +357,89 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
           __syncwarp();
           // ---- phase B: coalesced residual add + store
           const int ocol = (MODE == SG_EPI_GEGLU) ? (col0 >> 1) : col0;
+          [[maybe_unused]] float ccs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ccq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < kIter; ++i) {
             uint4 q = lds128(sc_addr(buf, i * kRpi + lane / kLpr, lane % kLpr));
-            if (okB[i]) {
-              if constexpr (MODE == SG_EPI_LINEAR) {
-                if (use_res) {
-                  const uint4 rq = res[ci][i];
-                  float2 a0 = unpack_bf16x2(q.x), a1 = unpack_bf16x2(q.y), a2 = unpack_bf16x2(q.z), a3 = unpack_bf16x2(q.w);
-                  float2 r0 = unpack_bf16x2(rq.x), r1 = unpack_bf16x2(rq.y), r2 = unpack_bf16x2(rq.z), r3 = unpack_bf16x2(rq.w);
-                  q.x = pack_bf16x2(fmaf(p.res_scale, r0.x, a0.x), fmaf(p.res_scale, r0.y, a0.y));
-                  q.y = pack_bf16x2(fmaf(p.res_scale, r1.x, a1.x), fmaf(p.res_scale, r1.y, a1.y));
-                  q.z = pack_bf16x2(fmaf(p.res_scale, r2.x, a2.x), fmaf(p.res_scale, r2.y, a2.y));
-                  q.w = pack_bf16x2(fmaf(p.res_scale, r3.x, a3.x), fmaf(p.res_scale, r3.y, a3.y));
+            if constexpr (MODE == SG_EPI_LINEAR) {
+             if (use_res || row_out || col_out) {  // kernel-uniform
+              float2 a0 = unpack_bf16x2(q.x), a1 = unpack_bf16x2(q.y), a2 = unpack_bf16x2(q.z), a3 = unpack_bf16x2(q.w);
+              if (use_res && okB[i]) {
+                const uint4 rq = res[ci][i];
+                float2 r0 = unpack_bf16x2(rq.x), r1 = unpack_bf16x2(rq.y), r2 = unpack_bf16x2(rq.z), r3 = unpack_bf16x2(rq.w);
+                a0.x = fmaf(p.res_scale, r0.x, a0.x); a0.y = fmaf(p.res_scale, r0.y, a0.y);
+                a1.x = fmaf(p.res_scale, r1.x, a1.x); a1.y = fmaf(p.res_scale, r1.y, a1.y);
+                a2.x = fmaf(p.res_scale, r2.x, a2.x); a2.y = fmaf(p.res_scale, r2.y, a2.y);
+                a3.x = fmaf(p.res_scale, r3.x, a3.x); a3.y = fmaf(p.res_scale, r3.y, a3.y);
+                q.x = pack_bf16x2(a0.x, a0.y);
+                q.y = pack_bf16x2(a1.x, a1.y);
+                q.z = pack_bf16x2(a2.x, a2.y);
+                q.w = pack_bf16x2(a3.x, a3.y);
+              }
+              if (row_out || col_out) {
+                const float fv[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+                if (row_out) {
+                  // this lane holds 8 of the row's 32 columns; the 4 lanes of a row are neighbours
+                  float s = 0.f, qq = 0.f;
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    s += fv[k];
+                    qq = fmaf(fv[k], fv[k], qq);
+                  }
+                  s += __shfl_xor_sync(0xffffffffu, s, 1);
+                  qq += __shfl_xor_sync(0xffffffffu, qq, 1);
+                  s += __shfl_xor_sync(0xffffffffu, s, 2);
+                  qq += __shfl_xor_sync(0xffffffffu, qq, 2);
+                  rs_acc[i] += s;
+                  rq_acc[i] += qq;
+                }
+                if (col_out && okB[i]) {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    ccs[k] += fv[k];
+                    ccq[k] = fmaf(fv[k], fv[k], ccq[k]);
+                  }
                 }
               }
-              *reinterpret_cast<uint4*>(p.out + mB[i] * p.ldo + ocol + (lane % kLpr) * 8) = q;
+             }
+            }
+            if (okB[i]) *reinterpret_cast<uint4*>(p.out + mB[i] * p.ldo + ocol + (lane % kLpr) * 8) = q;
+          }
+          if constexpr (MODE == SG_EPI_LINEAR) {
+            if (col_out) {
+              // lanes l, l+4, ..., l+28 hold the same 8 columns for different rows: fold them, lanes 0..3 store
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                for (int o = 4; o <= 16; o <<= 1) {
+                  ccs[k] += __shfl_xor_sync(0xffffffffu, ccs[k], o);
+                  ccq[k] += __shfl_xor_sync(0xffffffffu, ccq[k], o);
+                }
+              }
+              if (lane < 4) {
+                float4* dst = reinterpret_cast<float4*>(
+                    reinterpret_cast<float2*>(p.col_stats_out) + (static_cast<long long>(mt) * 4 + quarter) * p.N + col0 + lane * 8);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dst[k] = make_float4(ccs[2 * k], ccq[2 * k], ccs[2 * k + 1], ccq[2 * k + 1]);
+              }
             }
           }
           __syncwarp();  // phase-B reads done before the next chunk's phase-A writes
         }
+      }
+    }
+  }
+  if constexpr (MODE == SG_EPI_LINEAR) {
+    if (row_out) {
+      float2* dst = reinterpret_cast<float2*>(p.row_stats_out) + static_cast<long long>(nt * 2 + grp) * p.M;
+      if (tr) {
+        if ((lane & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (okB[i]) dst[mB[i]] = make_float2(rs_acc[i], rq_acc[i]);
+        }
+      } else if (row_ok) {
+        dst[(static_cast<long long>(n) * p.out_h + y) * p.out_w + x] = make_float2(rs_acc[0], rq_acc[0]);
       }
     }
   }

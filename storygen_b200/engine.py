@@ -5,13 +5,20 @@ the two are the same memory, so the reference's NCHW<->token permutes around eac
 (model/attention.py:103,117) do not exist here.  Weights are re-packed once per model (bf16, K-major,
 conv taps / shortcut / fused projections concatenated along K or N as the kernels consume them).
 
+Normalisation is fused into the GEMMs either side of it:
+  * LayerNorm never runs as a kernel: LN(x) W^T + b = rstd (x W'^T - mean csum) + b' with W' = W diag(gamma),
+    csum = row sums of W', b' = b + W beta (packed once); the GEMM that PRODUCES x emits per-row (sum, sumsq)
+    partials from its epilogue, the consuming GEMM multiplies the raw x and applies mean / rstd per row in its epilogue.
+  * GroupNorm statistics come from the producing GEMM's epilogue as per-channel partial sums (32-row blocks), reduced
+    by a tiny fixed-order kernel; only the apply(+SiLU, + channel concat) pass touches the activations.
+
 Launch sequence per ResnetBlock2D (6 kernels):
-    gn_stats, gn_apply+SiLU(+channel concat) -> conv3x3 GEMM (+bias +time embedding)
-    gn_stats, gn_apply+SiLU                  -> conv3x3 GEMM (+1x1 shortcut as extra K segments | +x)
-per Transformer2DModel (feature pass 16, denoise pass 19 kernels; + one text K/V GEMM per forward or per prompt):
-    GN -> proj_in GEMM -> LN1 -> QKV GEMM -> attention -> out-proj GEMM(+h) [= the tapped feature]
-    LN2(/LN4) -> Q GEMM, attention over the pre-projected text K/V [-> Q3 GEMM, image KV GEMM, attention]
-    out-proj GEMM over [a_text | a_image] (+2h)  -> LN3 -> FF1 GEMM(GEGLU) -> FF2 GEMM(+h) -> proj_out GEMM(+x)
+    gn_finalize, gn_apply+SiLU(+channel concat) -> conv3x3 GEMM (+bias +time embedding, emits GN partials)
+    gn_finalize, gn_apply+SiLU                  -> conv3x3 GEMM (+1x1 shortcut as extra K segments | +x, emits GN partials)
+per Transformer2DModel (feature pass 12, denoise pass 15 kernels; + one text K/V GEMM per forward or per prompt):
+    GN -> proj_in GEMM -> QKV GEMM (LN1 folded) -> attention -> out-proj GEMM(+h) [= the tapped feature]
+    Q GEMM (LN2 folded), attention over the pre-projected text K/V [-> Q3 GEMM (LN4 folded), image KV GEMM, attention]
+    out-proj GEMM over [a_text | a_image] (+2h) -> FF1 GEMM (LN3 folded, GEGLU) -> FF2 GEMM(+h) -> proj_out GEMM(+x)
 """
 from __future__ import annotations
 
@@ -24,6 +31,15 @@ from ._lib import SG_EPI_GEGLU, SG_EPI_NCHW_F32
 from .ops import BF16, Src, taps3x3
 
 F32 = torch.float32
+
+
+class Act:
+    """An NHWC activation (n, h, w, c) plus, when its producer emitted them, the per-channel GroupNorm partials
+    (sg_gemm col_stats_out) of the 32-row blocks of its pixel grid."""
+    __slots__ = ("t", "cs")
+
+    def __init__(self, t, cs=None):
+        self.t, self.cs = t, cs
 
 
 class UNetEngine:
@@ -47,6 +63,7 @@ class UNetEngine:
         if cfg.cross_attention_dim % 64:
             raise NotImplementedError("cross_attention_dim must be a multiple of 64")
         self._pack()
+        self.fuse_gn_stats = True  # GroupNorm statistics from the producing GEMM's epilogue (False: separate pass)
         self._stats = None      # workspace of the forward in flight
         self._own_stats = None  # engine-owned workspace for direct unet(...) calls (never handed to a captured graph)
 
@@ -78,30 +95,46 @@ class UNetEngine:
         d["w2"], d["b2"], d["shortcut"] = self._bf(w2), self._f32(b2), r.conv_shortcut is not None
         return d
 
+    def _fold_ln(self, w, b, norm, perm=None):
+        """LayerNorm folded into the Linear that follows it (model/attention.py:250,268,283,298):
+        LN(x) W^T + b = rstd (x W'^T - mean csum) + b';  returns (W' bf16, csum fp32, b' fp32)."""
+        w = w.detach().to(self.dev, F32)
+        g, beta = norm.weight.detach().to(self.dev, F32), norm.bias.detach().to(self.dev, F32)
+        wp = (w * g[None, :]).to(BF16)
+        csum = wp.to(F32).sum(1)  # of the ROUNDED weights the tensor core multiplies
+        bp = w @ beta
+        if b is not None:
+            bp = bp + b.detach().to(self.dev, F32)
+        if perm is not None:
+            wp, csum, bp = perm(wp), perm(csum), perm(bp)
+        return wp.contiguous(), csum.contiguous(), bp.contiguous()
+
     def _pack_transformer(self, t):
         blk = t.transformer_blocks[0]
         c = t.proj_in.weight.shape[0]
-        ln = lambda m: (self._f32(m.weight), self._f32(m.bias))
         d = dict(c=c, heads=t.num_attention_heads, hd=t.attention_head_dim)
         d["gn"] = (self._f32(t.norm.weight), self._f32(t.norm.bias))
         d["w_in"], d["b_in"] = self._bf(t.proj_in.weight.reshape(c, -1)), self._f32(t.proj_in.bias)
         d["w_out"], d["b_out"] = self._bf(t.proj_out.weight.reshape(t.proj_out.weight.shape[0], -1)), self._f32(t.proj_out.bias)
-        d["ln1"], d["ln2"], d["ln3"], d["ln4"] = ln(blk.norm1), ln(blk.norm2), ln(blk.norm3), ln(blk.norm4)
         a1, a2, a3 = blk.attn1, blk.attn2, blk.attn3
-        d["w_qkv1"] = self._bf(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0))
+        d["qkv1"] = self._fold_ln(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0), None, blk.norm1)
         d["w_o1"], d["b_o1"] = self._bf(a1.to_out[0].weight), self._f32(a1.to_out[0].bias)
-        d["w_q2"] = self._bf(a2.to_q.weight)
+        d["q2"] = self._fold_ln(a2.to_q.weight, None, blk.norm2)
         d["w_kv2"] = torch.cat([a2.to_k.weight.detach(), a2.to_v.weight.detach()], 0)  # fused across layers in _pack
         d["w_o2"], d["b_o2"] = self._bf(a2.to_out[0].weight), self._f32(a2.to_out[0].bias)
-        d["w_q3"] = self._bf(a3.to_q.weight)
+        d["q3"] = self._fold_ln(a3.to_q.weight, None, blk.norm4)
         d["w_kv3"] = self._bf(torch.cat([a3.to_k.weight, a3.to_v.weight], 0))
         d["w_o23"] = self._bf(torch.cat([a2.to_out[0].weight, a3.to_out[0].weight], 1))
         d["b_o23"] = self._f32(a2.to_out[0].bias.detach() + a3.to_out[0].bias.detach())
         # GEGLU: interleave [16 value rows | 16 gate rows] so one 32-column epilogue chunk holds both halves
         w, b = blk.ff.net[0].proj.weight.detach(), blk.ff.net[0].proj.bias.detach()
         half = w.shape[0] // 2
-        d["w_ff1"] = self._bf(torch.stack([w[:half].reshape(-1, 16, c), w[half:].reshape(-1, 16, c)], 1).reshape(2 * half, c))
-        d["b_ff1"] = self._f32(torch.stack([b[:half].reshape(-1, 16), b[half:].reshape(-1, 16)], 1).reshape(-1))
+
+        def interleave(v):  # rows [value | gate] -> blocks of [16 value rows | 16 gate rows]
+            tail = v.shape[1:]
+            return torch.stack([v[:half].reshape(-1, 16, *tail), v[half:].reshape(-1, 16, *tail)], 1).reshape(2 * half, *tail)
+
+        d["ff1"] = self._fold_ln(w, b, blk.norm3, perm=interleave)
         d["w_ff2"], d["b_ff2"] = self._bf(blk.ff.net[2].weight), self._f32(blk.ff.net[2].bias)
         return d
 
@@ -168,33 +201,50 @@ class UNetEngine:
     def _new(self, *shape, dtype=BF16):
         return torch.empty(shape, dtype=dtype, device=self.dev)
 
-    def _gn(self, x0, x1, n, hw, gamma_beta, eps, silu):
-        c = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+    def _new_act(self, n, h, w, c) -> Act:
+        """Output buffer of a GEMM on the (w, h, n) pixel grid + the buffer for its GroupNorm partials."""
+        blocks = ops.col_stat_blocks((w, h, n))[0] if self.fuse_gn_stats else 0
+        cs = torch.empty(blocks, c, 2, dtype=F32, device=self.dev) if blocks else None
+        return Act(self._new(n, h, w, c), cs)
+
+    def _gn(self, a0: Act, a1, gamma_beta, eps, silu):
+        """[SiLU](GroupNorm(concat_c(a0, a1))) -> (n, hw, c) tensor."""
+        n, h, w, c0 = a0.t.shape
+        hw = h * w
+        c = c0 + (a1.t.shape[-1] if a1 is not None else 0)
         out = self._new(n, hw, c)
-        ops.groupnorm(x0, x1, n, hw, self.groups, eps, gamma_beta[0], gamma_beta[1], silu, out, self._stats)
+        x0 = a0.t.view(n, hw, -1)
+        x1 = None if a1 is None else a1.t.view(n, hw, -1)
+        if a0.cs is not None and (a1 is None or a1.cs is not None):
+            _, tiles_xy, bn = ops.col_stat_blocks((w, h, n))
+            ops.groupnorm_from_parts(x0, a0.cs, x1, None if a1 is None else a1.cs, n, hw, tiles_xy, bn, self.groups, eps,
+                                     gamma_beta[0], gamma_beta[1], silu, out, self._new(n, self.groups, 2, dtype=F32))
+        else:  # a producer without statistics (fewer than 32 pixels per image and tile): separate statistics pass
+            ops.groupnorm(x0, x1, n, hw, self.groups, eps, gamma_beta[0], gamma_beta[1], silu, out, self._stats)
         return out
 
-    def _resnet(self, p, x0, x1, n, h, w, lane_bias):
-        """x = concat_c(x0, x1) as (n, h, w, c*) tensors.  Returns (n, h, w, cout)."""
-        hw, cout = h * w, p["cout"]
-        xn = self._gn(x0.view(n, hw, -1), None if x1 is None else x1.view(n, hw, -1), n, hw, p["gn1"], self.eps, True)
-        h1 = self._new(n, h, w, cout)
-        ops.gemm([Src.nhwc(xn.view(n, h, w, -1))], taps3x3(0, p["cin"]), (w, h, n), p["w1"], h1,
-                 lane_bias=lane_bias[:, p["temb_off"]:], ld_lane_bias=lane_bias.shape[1])
-        hn = self._gn(h1.view(n, hw, cout), None, n, hw, p["gn2"], self.eps, True)
-        out = self._new(n, h, w, cout)
+    def _resnet(self, p, a0: Act, a1, lane_bias) -> Act:
+        """x = concat_c(a0, a1).  Returns Act (n, h, w, cout)."""
+        n, h, w, _ = a0.t.shape
+        cout = p["cout"]
+        xn = self._gn(a0, a1, p["gn1"], self.eps, True)
+        h1 = self._new_act(n, h, w, cout)
+        ops.gemm([Src.nhwc(xn.view(n, h, w, -1))], taps3x3(0, p["cin"]), (w, h, n), p["w1"], h1.t,
+                 lane_bias=lane_bias[:, p["temb_off"]:], ld_lane_bias=lane_bias.shape[1], col_stats_out=h1.cs)
+        hn = self._gn(h1, None, p["gn2"], self.eps, True)
+        out = self._new_act(n, h, w, cout)
         srcs = [Src.nhwc(hn.view(n, h, w, cout))]
         segs = taps3x3(0, cout)
         residual = None
         if p["shortcut"]:
-            srcs.append(Src.nhwc(x0))
-            segs.append((1, 0, 0, 0, x0.shape[-1] // 64))
-            if x1 is not None:
-                srcs.append(Src.nhwc(x1))
-                segs.append((2, 0, 0, 0, x1.shape[-1] // 64))
+            srcs.append(Src.nhwc(a0.t))
+            segs.append((1, 0, 0, 0, a0.t.shape[-1] // 64))
+            if a1 is not None:
+                srcs.append(Src.nhwc(a1.t))
+                segs.append((2, 0, 0, 0, a1.t.shape[-1] // 64))
         else:
-            residual = x0
-        ops.gemm(srcs, segs, (w, h, n), p["w2"], out, bias=p["b2"], residual=residual)
+            residual = a0.t
+        ops.gemm(srcs, segs, (w, h, n), p["w2"], out.t, bias=p["b2"], residual=residual, col_stats_out=out.cs)
         return out
 
     def project_text(self, encoder_hidden_states, out=None):
@@ -207,42 +257,40 @@ class UNetEngine:
         with torch.cuda.device(self.dev):
             return ops.linear(text.view(n * L, d), self.w_kv2_all, out)
 
-    def _transformer(self, p, x, n, h, w, text_kv, n_text_tokens, image, kv_map, n_kv_lanes):
-        """x (n, h, w, c); text_kv (n * L, n_kv2) bf16 from project_text; image None or (n_kv, R*hw, c) bf16.
-        Returns (out (n, h, w, c), tap (n, hw, c))."""
+    def _transformer(self, p, xa: Act, text_kv, n_text_tokens, image, kv_map, n_kv_lanes):
+        """xa (n, h, w, c); text_kv (n * L, n_kv2) bf16 from project_text; image None or (n_kv, R*hw, c) bf16.
+        Returns (out Act (n, h, w, c), tap (n, hw, c))."""
+        n, h, w, _ = xa.t.shape
         hw, c, heads, hd = h * w, p["c"], p["heads"], p["hd"]
         m = n * hw
-        xn = self._gn(x.view(n, hw, c), None, n, hw, p["gn"], 1e-6, False)
-        h0 = self._new(m, c)
-        ops.linear(xn.view(m, c), p["w_in"], h0, bias=p["b_in"])
-        # --- self attention
-        n1 = self._new(m, c)
-        ops.layernorm(h0, 1e-5, p["ln1"][0], p["ln1"][1], n1)
+        x = xa.t
+        xn = self._gn(xa, None, p["gn"], 1e-6, False)
+
+        def row_stats(ncols):
+            return torch.empty(ops.row_stat_parts((m, 1, 1), ncols), m, 2, dtype=F32, device=self.dev)
+
+        h0, rs0 = self._new(m, c), row_stats(c)
+        ops.linear(xn.view(m, c), p["w_in"], h0, bias=p["b_in"], row_stats_out=rs0)
+        # --- self attention (LN1 folded into the QKV projection)
         qkv = self._new(m, 3 * c)
-        ops.linear(n1, p["w_qkv1"], qkv)
+        ops.linear(h0, p["qkv1"][0], qkv, bias=p["qkv1"][2], ln=(rs0, p["qkv1"][1], 1e-5))
         a1 = self._new(m, c)
         st = (hw * 3 * c, 3 * c)
         ops.attention(qkv, qkv[:, c:], qkv[:, 2 * c:], a1, n, heads, hd, hw, hw, st, st, st)
-        h1 = self._new(m, c)  # residual stream after self-attention == the tapped diffusion feature
-        ops.linear(a1, p["w_o1"], h1, bias=p["b_o1"], residual=h0)
-        # --- text (+ image) cross attention
-        n2 = self._new(m, c)
-        n4 = self._new(m, c) if image is not None else None
-        if image is not None:
-            ops.layernorm(h1, 1e-5, p["ln2"][0], p["ln2"][1], n2, p["ln4"][0], p["ln4"][1], n4)
-        else:
-            ops.layernorm(h1, 1e-5, p["ln2"][0], p["ln2"][1], n2)
+        h1, rs1 = self._new(m, c), row_stats(c)  # residual stream after self-attention == the tapped diffusion feature
+        ops.linear(a1, p["w_o1"], h1, bias=p["b_o1"], residual=h0, row_stats_out=rs1)
+        # --- text (+ image) cross attention (LN2 / LN4 folded into the Q projections)
         q2 = self._new(m, c)
-        ops.linear(n2, p["w_q2"], q2)
+        ops.linear(h1, p["q2"][0], q2, bias=p["q2"][2], ln=(rs1, p["q2"][1], 1e-5))
         L = n_text_tokens
         ld = text_kv.shape[1]
         kv2 = text_kv[:, p["kv2_off"]:]
         a2 = self._new(m, c)
         ops.attention(q2, kv2, kv2[:, c:], a2, n, heads, hd, hw, L, (hw * c, c), (L * ld, ld), (L * ld, ld))
-        h2 = self._new(m, c)
+        h2, rs2 = self._new(m, c), row_stats(c)
         if image is not None:
             q3 = self._new(m, c)
-            ops.linear(n4, p["w_q3"], q3)
+            ops.linear(h1, p["q3"][0], q3, bias=p["q3"][2], ln=(rs1, p["q3"][1], 1e-5))
             nkv, nk = image.shape[0], image.shape[1]
             kv3 = self._new(nkv * nk, 2 * c)
             ops.linear(image.view(nkv * nk, c), p["w_kv3"], kv3)
@@ -251,36 +299,39 @@ class UNetEngine:
                           (nk * 2 * c, 2 * c), n_kv_lanes=nkv, kv_map=kv_map)
             # h_t + h_i = 2h + a_t + a_i  (model/attention.py:277,291,293): one GEMM over K = [a2 | a3]
             ops.gemm([Src.rows(a2), Src.rows(a3)], [(0, 0, 0, 0, c // 64), (1, 0, 0, 0, c // 64)], (m, 1, 1),
-                     p["w_o23"], h2, bias=p["b_o23"], residual=h1, res_scale=2.0)
+                     p["w_o23"], h2, bias=p["b_o23"], residual=h1, res_scale=2.0, row_stats_out=rs2)
         else:
-            ops.linear(a2, p["w_o2"], h2, bias=p["b_o2"], residual=h1)
-        # --- feed forward
-        n3 = self._new(m, c)
-        ops.layernorm(h2, 1e-5, p["ln3"][0], p["ln3"][1], n3)
+            ops.linear(a2, p["w_o2"], h2, bias=p["b_o2"], residual=h1, row_stats_out=rs2)
+        # --- feed forward (LN3 folded into the GEGLU projection)
         ff = self._new(m, 4 * c)
-        ops.linear(n3, p["w_ff1"], ff, bias=p["b_ff1"], mode=SG_EPI_GEGLU)
+        ops.linear(h2, p["ff1"][0], ff, bias=p["ff1"][2], mode=SG_EPI_GEGLU, ln=(rs2, p["ff1"][1], 1e-5))
         h3 = self._new(m, c)
         ops.linear(ff, p["w_ff2"], h3, bias=p["b_ff2"], residual=h2)
-        out = self._new(n, h, w, x.shape[-1])
-        ops.linear(h3, p["w_out"], out.view(m, -1), bias=p["b_out"], residual=x.view(m, -1))
+        # proj_out is a (m, 1, 1)-grid GEMM whose rows ARE the pixels of the (w, h, n) grid; its GroupNorm partials must
+        # follow that grid's tiling, so it runs on the pixel grid (1x1 conv form)
+        out = self._new_act(n, h, w, x.shape[-1])
+        ops.gemm([Src.nhwc(h3.view(n, h, w, c))], [(0, 0, 0, 0, c // 64)], (w, h, n), p["w_out"], out.t, bias=p["b_out"],
+                 residual=x.view(m, -1), col_stats_out=out.cs)
         return out, h1.view(n, hw, c)
 
-    def _downsample(self, wb, x, n, h, w):
-        c = x.shape[-1]
-        out = self._new(n, h // 2, w // 2, c)
+    def _downsample(self, wb, xa: Act) -> Act:
+        x = xa.t
+        n, h, w, c = x.shape
+        out = self._new_act(n, h // 2, w // 2, c)
         srcs = [Src.nhwc_phase(x, py, px) for py in range(2) for px in range(2)]
         # input row 2*oy + ky - 1: ky=0 -> odd phase shifted by -1, ky=1 -> even phase, ky=2 -> odd phase
         ph, sh = (1, 0, 1), (-1, 0, 0)
         segs = [(ph[ky] * 2 + ph[kx], sh[kx], sh[ky], 0, c // 64) for ky in range(3) for kx in range(3)]
-        ops.gemm(srcs, segs, (w // 2, h // 2, n), wb[0], out, bias=wb[1])
+        ops.gemm(srcs, segs, (w // 2, h // 2, n), wb[0], out.t, bias=wb[1], col_stats_out=out.cs)
         return out
 
-    def _upsample(self, wb, x, n, h, w):
-        c = x.shape[-1]
+    def _upsample(self, wb, xa: Act) -> Act:
+        x = xa.t
+        n, h, w, c = x.shape
         up = self._new(n, 2 * h, 2 * w, c)
         ops.upsample2x(x, up)
-        out = self._new(n, 2 * h, 2 * w, c)
-        ops.gemm([Src.nhwc(up)], taps3x3(0, c), (2 * w, 2 * h, n), wb[0], out, bias=wb[1])
+        out = self._new_act(n, 2 * h, 2 * w, c)
+        ops.gemm([Src.nhwc(up)], taps3x3(0, c), (2 * w, 2 * h, n), wb[0], out.t, bias=wb[1], col_stats_out=out.cs)
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -341,7 +392,7 @@ class UNetEngine:
 
         taps: Dict[str, torch.Tensor] = {}
 
-        def attn(p, x, hh, ww, key):
+        def attn(p, xa, hh, ww, key):
             image = None
             if img is not None:
                 if key not in img:
@@ -352,38 +403,41 @@ class UNetEngine:
                                      f"(lanes, R*{hh * ww}, {p['c']})")
                 if kv_map is None and image.shape[0] != n:
                     raise ValueError(f"image_hidden_states[{key!r}] has {image.shape[0]} lanes for a batch of {n}")
-            out, tap = self._transformer(p, x, n, hh, ww, text_kv, L, image, kv_map, 0)
+            out, tap = self._transformer(p, xa, text_kv, L, image, kv_map, 0)
             if img is None:
                 taps[key] = tap
             return out
 
         patches = ops.im2col3x3_nchw(sample, self._new(n * h * w, 64))
-        x = self._new(n, h, w, boc0)
-        ops.linear(patches, self.conv_in[0], x.view(n * h * w, boc0), bias=self.conv_in[1])
+        x = self._new_act(n, h, w, boc0)
+        # conv_in as a K = 64 GEMM over the pre-gathered patches, on the pixel grid (so that its GroupNorm partials
+        # follow the grid's tiling)
+        ops.gemm([Src.nhwc(patches.view(n, h, w, 64))], [(0, 0, 0, 0, 1)], (w, h, n), self.conv_in[0], x.t,
+                 bias=self.conv_in[1], col_stats_out=x.cs)
         skips = [x]
         hh, ww = h, w
         for i, blk in enumerate(self.down):
             for j, rp in enumerate(blk["res"]):
-                x = self._resnet(rp, x, None, n, hh, ww, lane_bias)
+                x = self._resnet(rp, x, None, lane_bias)
                 if blk["attn"] is not None:
                     x = attn(blk["attn"][j], x, hh, ww, f"down_{i + 1}_{j + 1}")
                 skips.append(x)
             if blk["down"] is not None:
-                x = self._downsample(blk["down"], x, n, hh, ww)
+                x = self._downsample(blk["down"], x)
                 hh, ww = hh // 2, ww // 2
                 skips.append(x)
-        x = self._resnet(self.mid["res"][0], x, None, n, hh, ww, lane_bias)
+        x = self._resnet(self.mid["res"][0], x, None, lane_bias)
         x = attn(self.mid["attn"][0], x, hh, ww, "mid")
-        x = self._resnet(self.mid["res"][1], x, None, n, hh, ww, lane_bias)
+        x = self._resnet(self.mid["res"][1], x, None, lane_bias)
         for i, blk in enumerate(self.up):
             for j, rp in enumerate(blk["res"]):
-                x = self._resnet(rp, x, skips.pop(), n, hh, ww, lane_bias)
+                x = self._resnet(rp, x, skips.pop(), lane_bias)
                 if blk["attn"] is not None:
                     x = attn(blk["attn"][j], x, hh, ww, f"up_{i}_{j + 1}")
             if blk["up"] is not None:
-                x = self._upsample(blk["up"], x, n, hh, ww)
+                x = self._upsample(blk["up"], x)
                 hh, ww = hh * 2, ww * 2
-        xn = self._gn(x.view(n, hh * ww, -1), None, n, hh * ww, self.norm_out, self.eps, True)
+        xn = self._gn(x, None, self.norm_out, self.eps, True)
         out = self._new(n, self.conv_out[2], hh, ww, dtype=F32)
         ops.gemm([Src.nhwc(xn.view(n, hh, ww, -1))], taps3x3(0, xn.shape[-1]), (ww, hh, n), self.conv_out[0], out,
                  bias=self.conv_out[1], mode=SG_EPI_NCHW_F32, out_channels=self.conv_out[2])

@@ -71,12 +71,47 @@ def tile_box(w: int, h: int, n: int) -> Tuple[int, int, int]:
     return bw, bh, 128 // (bw * bh)
 
 
+_PARTS_CACHE = {}
+
+
+def row_stat_parts(grid: Tuple[int, int, int], n_cols: int) -> int:
+    """Number of row-statistics partials a GEMM with this output grid and N writes per row (sg_gemm_row_stat_parts)."""
+    key = (grid, n_cols, torch.cuda.current_device())
+    v = _PARTS_CACHE.get(key)
+    if v is None:
+        a = SgGemmArgs()
+        a.out_w, a.out_h, a.out_n = grid
+        a.bw, a.bh, a.bn = tile_box(*grid)
+        a.N = n_cols
+        v = _lib.load().sg_gemm_row_stat_parts(C.byref(a))
+        if v < 0:
+            _lib.check(v, "sg_gemm_row_stat_parts")
+        _PARTS_CACHE[key] = v
+    return v
+
+
+def col_stat_blocks(grid: Tuple[int, int, int]) -> Tuple[int, int, int]:
+    """(number of 32-row blocks, tiles_xy, imgs_per_tile) of the per-channel statistics a GEMM on this output grid
+    writes (sg_gemm col_stats_out), or (0, 0, 0) when a 32-row quarter would span two images (fewer than 32 pixels per
+    image and tile: the consumer then falls back to sg_groupnorm_stats)."""
+    w, h, n = grid
+    bw, bh, bn = tile_box(w, h, n)
+    if (bw * bh) % 32 != 0 or bn > 4:
+        return 0, 0, 0
+    tx, ty, tn = -(-w // bw), -(-h // bh), -(-n // bn)
+    return tx * ty * tn * 4, tx * ty, bn
+
+
 def gemm(srcs: Sequence[Src], segs: Sequence[Tuple[int, int, int, int, int]], grid: Tuple[int, int, int],
          weight: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None,
          lane_bias: Optional[torch.Tensor] = None, ld_lane_bias: int = 0, residual: Optional[torch.Tensor] = None,
-         res_scale: float = 1.0, mode: int = SG_EPI_LINEAR, out_channels: int = 0) -> torch.Tensor:
+         res_scale: float = 1.0, mode: int = SG_EPI_LINEAR, out_channels: int = 0,
+         row_stats_out: Optional[torch.Tensor] = None, ln=None, col_stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[m, :] = epilogue(sum_k A[m, k] W[:, k]); see include/storygen_b200.h (sg_gemm).
-    segs: (src, dx, dy, c0, nkb); grid: (out_w, out_h, out_n); weight: bf16 [N, Ktot]."""
+    segs: (src, dx, dy, c0, nkb); grid: (out_w, out_h, out_n); weight: bf16 [N, Ktot].
+    row_stats_out: fp32 (row_stat_parts(grid, N), M, 2) receiving the output's per-row LayerNorm partials;
+    ln = (stats (parts, M, 2), csum (N,), eps): apply LayerNorm of the A rows in the epilogue (weight pre-scaled by gamma);
+    col_stats_out: fp32 (col_stat_blocks(grid)[0], N, 2) receiving the output's per-channel GroupNorm partials."""
     a = SgGemmArgs()
     a.num_src = len(srcs)
     for i, s in enumerate(srcs):
@@ -103,6 +138,19 @@ def gemm(srcs: Sequence[Src], segs: Sequence[Tuple[int, int, int, int, int]], gr
     a.ldr = residual.shape[-1] if residual is not None else 0
     a.out = out.data_ptr()
     a.ldo = out.shape[-1]
+    if row_stats_out is not None:
+        _req(row_stats_out, torch.float32, "row_stats_out")
+        a.row_stats_out = row_stats_out.data_ptr()
+    if col_stats_out is not None:
+        _req(col_stats_out, torch.float32, "col_stats_out")
+        a.col_stats_out = col_stats_out.data_ptr()
+    if ln is not None:
+        st, csum, eps = ln
+        _req(st, torch.float32, "ln stats")
+        _req(csum, torch.float32, "ln csum")
+        if st.shape[1] != grid[0] * grid[1] * grid[2] or csum.numel() != weight.shape[0]:
+            raise ValueError("ln statistics / csum do not match the GEMM's rows / columns")
+        a.ln_stats, a.ln_csum, a.ln_parts, a.ln_eps = st.data_ptr(), csum.data_ptr(), st.shape[0], eps
     if TRACE is not None:
         TRACE.append(("gemm", grid[0] * grid[1] * grid[2], int(a.N), int(a.Ktot), len(segs), mode))
     _lib.check(_lib.load().sg_gemm(C.byref(a), _stream()), "sg_gemm")
@@ -110,11 +158,11 @@ def gemm(srcs: Sequence[Src], segs: Sequence[Tuple[int, int, int, int, int]], gr
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, out: torch.Tensor, bias=None, residual=None, res_scale=1.0,
-           mode=SG_EPI_LINEAR) -> torch.Tensor:
+           mode=SG_EPI_LINEAR, row_stats_out=None, ln=None, col_stats_out=None) -> torch.Tensor:
     """x (M, K) bf16 @ weight (N, K)^T with the fused epilogue."""
     m, k = x.shape
     return gemm([Src.rows(x)], [(0, 0, 0, 0, k // 64)], (m, 1, 1), weight, out, bias=bias, residual=residual,
-                res_scale=res_scale, mode=mode)
+                res_scale=res_scale, mode=mode, row_stats_out=row_stats_out, ln=ln, col_stats_out=col_stats_out)
 
 
 def taps3x3(src: int, cin: int, c0: int = 0) -> List[Tuple[int, int, int, int, int]]:
@@ -154,6 +202,22 @@ def groupnorm(x0: torch.Tensor, x1: Optional[torch.Tensor], n: int, hw: int, gro
     _lib.check(lib.sg_groupnorm_apply(x0.data_ptr(), c0, _ptr(x1), c1, n, hw, groups, eps, stats.data_ptr(),
                                       gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(), _stream()),
                "sg_groupnorm_apply")
+    return out
+
+
+def groupnorm_from_parts(x0: torch.Tensor, parts0: torch.Tensor, x1: Optional[torch.Tensor], parts1: Optional[torch.Tensor],
+                         n: int, hw: int, tiles_xy: int, imgs_per_tile: int, groups: int, eps: float, gamma: torch.Tensor,
+                         beta: torch.Tensor, silu: bool, out: torch.Tensor, mean_rstd: torch.Tensor):
+    """y = [SiLU](GroupNorm(concat_c(x0, x1))) with the statistics the PRODUCING GEMMs emitted (col_stats_out): one tiny
+    reduction kernel (fixed order, fp64) + the apply pass; no pass over the activations for the statistics."""
+    lib = _lib.load()
+    c0 = x0.shape[-1]
+    c1 = x1.shape[-1] if x1 is not None else 0
+    _lib.check(lib.sg_groupnorm_finalize(parts0.data_ptr(), c0, _ptr(parts1), c1, n, hw, tiles_xy, imgs_per_tile, groups,
+                                         eps, mean_rstd.data_ptr(), _stream()), "sg_groupnorm_finalize")
+    _lib.check(lib.sg_groupnorm_apply_ms(x0.data_ptr(), c0, _ptr(x1), c1, n, hw, groups, mean_rstd.data_ptr(),
+                                         gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(), _stream()),
+               "sg_groupnorm_apply_ms")
     return out
 
 

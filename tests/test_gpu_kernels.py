@@ -247,3 +247,91 @@ def test_upsample_conv_in_out_and_scheduler_kernels():
     e = u + 3.5 * (i - u) + 7.0 * (al - i)
     x0 = (l0 - (1 - 0.3) ** 0.5 * e) / 0.3 ** 0.5
     assert torch.allclose(lat, 0.35 ** 0.5 * x0 + (1 - 0.35) ** 0.5 * e, atol=1e-4, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused normalisation hooks of sg_gemm (ABI 8): LayerNorm folded into producer / consumer GEMMs, GroupNorm statistics
+# from the producing GEMM's epilogue
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,k,n,kprod", [(4096, 320, 960, 320), (1000, 640, 640, 2560), (300, 1280, 1280, 1280)])
+def test_layernorm_folded_into_producer_and_consumer_gemms(m, k, n, kprod):
+    """x = A W0^T + b0 + r (producer, emits per-row partials: transposed epilogue for small K, direct for large K);
+    y = LN(x) W^T + b (consumer, raw x with gamma-scaled weights, mean / rstd applied per row in the epilogue)."""
+    a, w0 = rnd(m, kprod, seed=1), rnd(k, kprod, scale=kprod ** -0.5, seed=2)
+    b0, r = rnd(k, seed=3, dtype=torch.float32), rnd(m, k, seed=4)
+    x = torch.empty(m, k, dtype=BF16, device=DEV)
+    rs = torch.empty(ops.row_stat_parts((m, 1, 1), k), m, 2, dtype=torch.float32, device=DEV)
+    ops.linear(a, w0, x, bias=b0, residual=r, res_scale=2.0, row_stats_out=rs)
+    xf = x.float()
+    tot = rs.sum(0)  # (m, 2): sum, sumsq of every row
+    assert torch.allclose(tot[:, 0], xf.sum(1), rtol=2e-3, atol=0.3)
+    assert torch.allclose(tot[:, 1], (xf * xf).sum(1), rtol=4e-3, atol=0.5)
+    g = torch.Generator("cpu").manual_seed(9)
+    w = (torch.randn(n, k, generator=g) * k ** -0.5).to(DEV)
+    b = (torch.randn(n, generator=g) * 0.1).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(k, generator=g)).to(DEV)
+    beta = (0.05 * torch.randn(k, generator=g)).to(DEV)
+    wp = (w * gamma[None, :]).to(BF16)
+    csum, bp = wp.float().sum(1).contiguous(), (w @ beta + b).contiguous()
+    y = torch.empty(m, n, dtype=BF16, device=DEV)
+    ops.linear(x, wp, y, bias=bp, ln=(rs, csum, 1e-5))
+    ref = F.layer_norm(xf, (k,), gamma, beta, 1e-5) @ w.T + b
+    close(y, ref, rel=0.02, abs_=0.03)
+
+
+def test_layernorm_folded_geglu_consumer():
+    m, c = 512, 320
+    x = rnd(m, c, seed=1)
+    rs = torch.empty(ops.row_stat_parts((m, 1, 1), c), m, 2, dtype=torch.float32, device=DEV)
+    eye = torch.eye(c).to(BF16).to(DEV)
+    x2 = torch.empty_like(x)
+    ops.linear(x, eye, x2, row_stats_out=rs)  # identity producer: x2 == x, emits the row partials
+    assert torch.equal(x2, x)
+    g = torch.Generator("cpu").manual_seed(5)
+    w = (torch.randn(8 * c, c, generator=g) * c ** -0.5).to(DEV)
+    b = (torch.randn(8 * c, generator=g) * 0.1).to(DEV)
+    gamma, beta = (1 + 0.1 * torch.randn(c, generator=g)).to(DEV), (0.05 * torch.randn(c, generator=g)).to(DEV)
+    half = 4 * c
+    il = lambda v: torch.stack([v[:half].reshape(-1, 16, *v.shape[1:]), v[half:].reshape(-1, 16, *v.shape[1:])], 1).reshape(2 * half, *v.shape[1:])
+    wp = (w * gamma[None, :]).to(BF16)
+    out = torch.empty(m, half, dtype=BF16, device=DEV)
+    ops.linear(x, il(wp).contiguous(), out, bias=il(w @ beta + b).contiguous(), mode=_lib.SG_EPI_GEGLU,
+               ln=(rs, il(wp.float().sum(1)).contiguous(), 1e-5))
+    y = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5) @ w.T + b
+    close(out, y[:, :half] * F.gelu(y[:, half:]), rel=0.02, abs_=0.03)
+
+
+@pytest.mark.parametrize("n,h,w,c0,c1,offset", [(3, 64, 64, 320, 0, 0.0), (2, 32, 32, 640, 320, 0.0), (3, 8, 8, 1280, 1280, 0.0),
+                                               (2, 16, 16, 1280, 640, 0.0), (2, 32, 32, 320, 0, 40.0)])
+def test_groupnorm_from_producer_statistics(n, h, w, c0, c1, offset):
+    """GroupNorm(+SiLU) over concat(x0, x1) with the statistics the producing GEMMs emitted (3x3 conv: direct epilogue;
+    1x1 conv: transposed epilogue), against torch.group_norm of the bf16 tensors.  offset: |mean| >> std (the fp64
+    finalisation must not cancel)."""
+    groups, hw = 32, h * w
+    blocks, tiles_xy, bn = ops.col_stat_blocks((w, h, n))
+    assert blocks > 0
+
+    def produce(c, k, seed, conv3):
+        a = rnd(n, h, w, k, seed=seed)
+        bias = (rnd(c, seed=seed + 1, dtype=torch.float32) + offset).contiguous()
+        out = torch.empty(n, h, w, c, dtype=BF16, device=DEV)
+        cs = torch.empty(blocks, c, 2, dtype=torch.float32, device=DEV)
+        if conv3:
+            wt = rnd(c, 9 * k, scale=(9 * k) ** -0.5, seed=seed + 2)
+            ops.gemm([Src.nhwc(a)], taps3x3(0, k), (w, h, n), wt, out, bias=bias, col_stats_out=cs)
+        else:
+            wt = rnd(c, k, scale=k ** -0.5, seed=seed + 2)
+            ops.gemm([Src.nhwc(a)], [(0, 0, 0, 0, k // 64)], (w, h, n), wt, out, bias=bias, col_stats_out=cs)
+        return out, cs
+
+    x0, cs0 = produce(c0, 320, 10, True)
+    x1, cs1 = produce(c1, 128, 20, False) if c1 else (None, None)
+    c = c0 + c1
+    gamma, beta = rnd(c, seed=5, dtype=torch.float32) * 0.2 + 1.0, rnd(c, seed=6, dtype=torch.float32) * 0.1
+    out = torch.empty(n, hw, c, dtype=BF16, device=DEV)
+    mr = torch.empty(n, groups, 2, dtype=torch.float32, device=DEV)
+    ops.groupnorm_from_parts(x0.view(n, hw, c0), cs0, None if x1 is None else x1.view(n, hw, c1), cs1, n, hw, tiles_xy, bn,
+                             groups, 1e-5, gamma, beta, True, out, mr)
+    xcat = x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], -1)
+    ref = F.silu(F.group_norm(xcat.permute(0, 3, 1, 2), groups, gamma, beta, 1e-5)).permute(0, 2, 3, 1).reshape(n, hw, c)
+    close(out, ref, rel=0.015, abs_=0.03)
