@@ -42,6 +42,8 @@ if ROOT not in sys.path:
 GF_FEATURE_PASS = 803.3
 GF_DENOISE_PASS = {1: 976.9, 3: 1273.1, 5: 1569.3}
 GF_ATTN3_KV_PROJ_PER_FRAME = 25.6  # attn3 to_k/to_v over one prior frame's 16 tapped maps, per K/V lane
+GF_UPSAMPLE_CONVS = 67.95  # the 3 Upsample2D convs of one UNet call (2*256*1280*11520 + 2*1024*1280*11520 + 2*4096*640*5760)
+UPSAMPLE_EXECUTED_FRACTION = 4.0 / 9.0  # run as four 2x2-tap sub-pixel convolutions of the low-resolution tensor
 
 
 def gf_denoise(R: int) -> float:
@@ -55,9 +57,11 @@ def tflop_per_image_reference(R: int, steps: int) -> float:
 
 def tflop_per_image_executed(R: int, steps: int) -> float:
     """What THIS path executes per image: feature passes on 2 of the 3 CFG lanes (the third duplicates the second,
-    model/pipeline.py:429-430), 3 denoise lanes of which two share one attn3 K/V projection (kv_map)."""
+    model/pipeline.py:429-430), 3 denoise lanes of which two share one attn3 K/V projection (kv_map), and the
+    up-sampling convolutions as sub-pixel phases (4/9 of their dense FLOPs)."""
     feature_lanes, denoise_lanes, kv_lanes = 2, 3, 2
-    per_step = feature_lanes * R * GF_FEATURE_PASS + denoise_lanes * gf_denoise(R) \
+    up_saved = GF_UPSAMPLE_CONVS * (1.0 - UPSAMPLE_EXECUTED_FRACTION)  # per lane and UNet call
+    per_step = feature_lanes * R * (GF_FEATURE_PASS - up_saved) + denoise_lanes * (gf_denoise(R) - up_saved) \
         - (denoise_lanes - kv_lanes) * R * GF_ATTN3_KV_PROJ_PER_FRAME
     return steps * per_step / 1e3
 
@@ -490,7 +494,8 @@ def run_ours(args, rank, local_rank, world):
                                           "tflop_per_image_reference_equivalent": tf_ref,
                                           "work_removed_speedup": tf_ref / tf_exec,
                                           "note": "executed = 2R feature lanes + 3 denoise lanes - 1 shared attn3 K/V projection "
-                                                  "per image-step; the reference executes 3R + 3 lanes"},
+                                                  "per image-step, up-sampling convs at 4/9 (sub-pixel phases); the reference "
+                                                  "executes 3R + 3 lanes"},
                                 "ms_per_denoising_step_graph": ms_denoising_step, "eager_unet": eager},
             "cpu_baseline": cpu,
             "parity": parity,

@@ -115,6 +115,12 @@ typedef struct sg_gemm_args {
   float ln_eps;
   float* col_stats_out;  /* fp32 [M tiles * 4][N][2]: per (128-row tile, 32-row quarter, output channel) partial
                             (sum, sumsq) over the quarter's valid rows; modes LINEAR only                       */
+  /* Strided output (LINEAR / GEGLU): element (n, y, x, col) is stored at out + n*out_stride_n + y*out_stride_h +
+   * x*out_stride_w + col; all zero = dense rows of ldo elements.  Lets the four sub-pixel phases of
+   * "nearest 2x up-sample -> conv3x3" (model/unet_2d_blocks.py:581-584 Upsample2D) be computed as four 2x2-tap
+   * convolutions of the LOW-resolution tensor with pre-summed weights, each writing every second pixel of the
+   * output: 4/9 of the FLOPs and no up-sampled tensor. */
+  int64_t out_stride_w, out_stride_h, out_stride_n;
 } sg_gemm_args;
 
 int sg_gemm(const sg_gemm_args* args, void* stream);
@@ -167,18 +173,26 @@ int sg_groupnorm_apply(const void* x0, int32_t c0, const void* x1, int32_t c1, i
                        const float* beta, int32_t silu, void* y, void* stream);
 
 /* GroupNorm from producer-side statistics (no separate pass over the activations).
- * sg_groupnorm_finalize: reduces the col_stats_out partials of up to two producing GEMMs (the channel-concat x0 | x1
- * of the skip connections, model/unet_2d_blocks.py:609,626,716) to mean_rstd[n_img][groups][2], in a fixed order
- * (deterministic), accumulating in fp64 so that E[x^2] - mean^2 does not cancel for channels with |mean| >> std.
- * parts_i: the col_stats_out buffer of source i, [(M tiles) * 4][c_i][2].  Both sources were produced on the same
- * output pixel grid, tiled in boxes of bw x bh x bn pixels (bw * bh * bn == 128): image n owns the tiles
- * [ (n / bn) * tiles_xy, (n / bn + 1) * tiles_xy ) and, inside each, the 4 / bn quarters starting at (n % bn) * (4 / bn);
- * pass tiles_xy = (tiles along x) * (tiles along y) and imgs_per_tile = bn (1, 2 or 4: a 32-row quarter never spans
- * two images, i.e. hw >= 32).
+ * sg_groupnorm_finalize: reduces the col_stats_out partials of the GEMMs that produced x0 and x1 (the channel-concat
+ * x0 | x1 of the skip connections, model/unet_2d_blocks.py:609,626,716) to mean_rstd[n_img][groups][2], in a fixed
+ * order (deterministic), accumulating in fp64 so that E[x^2] - mean^2 does not cancel for channels with |mean| >> std.
+ * Source i is described by sg_gn_parts: `parts` = `reps` consecutive col_stats_out buffers [(M tiles) * 4][c][2] of GEMMs
+ * that tiled their (identical) output pixel grids in boxes of bw x bh x bn pixels (bw * bh * bn == 128); image n owns the
+ * tiles [ (n / bn) * tiles_xy, (n / bn + 1) * tiles_xy ) and, inside each, the 4 / bn quarters starting at
+ * (n % bn) * (4 / bn): tiles_xy = (tiles along x) * (tiles along y), imgs_per_tile = bn (1, 2 or 4: a 32-row quarter never
+ * spans two images).  reps > 1: the tensor was written by several GEMMs (the 4 sub-pixel phases of an up-sampling conv),
+ * each covering hw / reps pixels of every image.
  * sg_groupnorm_apply_ms: y = [SiLU]((x - mean) * rstd * gamma + beta) with those statistics. */
-int sg_groupnorm_finalize(const float* parts0, int32_t c0, const float* parts1, int32_t c1, int32_t n_img, int32_t hw,
-                          int32_t tiles_xy, int32_t imgs_per_tile, int32_t groups, float eps, float* mean_rstd,
-                          void* stream);
+typedef struct sg_gn_parts {
+  const float* parts;
+  int32_t c;             /* channels of this source                */
+  int32_t tiles_xy;
+  int32_t imgs_per_tile;
+  int32_t reps;
+  int32_t m_tiles;       /* M tiles of ONE producing GEMM (stride between the `reps` buffers = m_tiles * 4 * c * 2 floats) */
+} sg_gn_parts;
+int sg_groupnorm_finalize(const sg_gn_parts* src0, const sg_gn_parts* src1 /* or NULL */, int32_t n_img, int32_t hw,
+                          int32_t groups, float eps, float* mean_rstd, void* stream);
 int sg_groupnorm_apply_ms(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img, int32_t hw,
                           int32_t groups, const float* mean_rstd, const float* gamma, const float* beta,
                           int32_t silu, void* y, void* stream);

@@ -16,3 +16,5 @@ echo "bench rc=$?" >> gpurun_out/b_bench.err
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/b_launches.csv python scripts/profile_step.py > gpurun_out/b_prof.log 2>&1
 tail -3 gpurun_out/b_selftest.log; tail -4 gpurun_out/b_pytest_gpu.log; cat gpurun_out/b_attn_bench.log; head -c 300 gpurun_out/b_bench.json; tail -2 gpurun_out/b_bench.err
+timeout 300 python scripts/power_probe.py > gpurun_out/b_power.log 2>&1
+cat gpurun_out/b_power.log

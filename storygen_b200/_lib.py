@@ -44,7 +44,13 @@ class SgGemmArgs(C.Structure):
                 ("lane_bias", C.c_void_p), ("ld_lane_bias", C.c_int64), ("residual", C.c_void_p),
                 ("ldr", C.c_int64), ("out", C.c_void_p), ("ldo", C.c_int64), ("debug_timeline", C.c_void_p),
                 ("row_stats_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_csum", C.c_void_p),
-                ("ln_parts", C.c_int32), ("ln_eps", C.c_float), ("col_stats_out", C.c_void_p)]
+                ("ln_parts", C.c_int32), ("ln_eps", C.c_float), ("col_stats_out", C.c_void_p),
+                ("out_stride_w", C.c_int64), ("out_stride_h", C.c_int64), ("out_stride_n", C.c_int64)]
+
+
+class SgGnParts(C.Structure):
+    _fields_ = [("parts", C.c_void_p), ("c", C.c_int32), ("tiles_xy", C.c_int32), ("imgs_per_tile", C.c_int32),
+                ("reps", C.c_int32), ("m_tiles", C.c_int32)]
 
 
 class SgAttnArgs(C.Structure):
@@ -91,7 +97,7 @@ def load():
     lib.sg_groupnorm_ws_floats.argtypes = [i32, i32]
     lib.sg_groupnorm_stats.argtypes = [vp, i32, vp, i32, i32, i32, i32, f32, vp, vp]
     lib.sg_groupnorm_apply.argtypes = [vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, vp, i32, vp, vp]
-    lib.sg_groupnorm_finalize.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp]
+    lib.sg_groupnorm_finalize.argtypes = [C.POINTER(SgGnParts), C.POINTER(SgGnParts), i32, i32, i32, f32, vp, vp]
     lib.sg_groupnorm_apply_ms.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]
     lib.sg_layernorm.argtypes = [vp, i64, i32, f32, vp, vp, vp, vp, vp, vp, vp]
     lib.sg_timestep_features.argtypes = [vp, i32, i32, vp, vp]

@@ -181,24 +181,39 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x0, int c0, const bf16*
 // partials of image n / group g to (mean, rstd).  One block per (group, image); every thread sums a fixed subset in a
 // fixed order and the block tree is fixed, so the result is deterministic; fp64 accumulation keeps E[x^2] - mean^2
 // from cancelling when |mean| >> std.
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float2* __restrict__ parts0, int c0,
-                                                          const float2* __restrict__ parts1, int c1, int hw,
-                                                          int tiles_xy, int bn, int groups, float eps,
+struct GnSrc {
+  const float2* parts;
+  int c, tiles_xy, bn, reps, m_tiles;
+};
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const GnSrc s0, const GnSrc s1, int hw, int groups, float eps,
                                                           float2* __restrict__ mean_rstd) {
   __shared__ double s_s[128], s_q[128];
   const int g = blockIdx.x, n = blockIdx.y;
-  const int C = c0 + c1, cpg = C / groups;
-  const int nq = 4 / bn, q0 = (n % bn) * nq;
-  const long long tile0 = static_cast<long long>(n / bn) * tiles_xy;
-  const int items = tiles_xy * nq * cpg;
+  const int C = s0.c + s1.c, cpg = C / groups;
+  const int ch_lo = g * cpg, ch_hi = ch_lo + cpg;
   double s = 0.0, q = 0.0;
-  for (int it = threadIdx.x; it < items; it += 128) {
-    const int ch = g * cpg + it % cpg;
-    const int bi = it / cpg;
-    const long long blk = (tile0 + bi / nq) * 4 + q0 + bi % nq;
-    const float2 e = (ch < c0) ? __ldg(parts0 + blk * c0 + ch) : __ldg(parts1 + blk * c1 + (ch - c0));
-    s += static_cast<double>(e.x);
-    q += static_cast<double>(e.y);
+#pragma unroll
+  for (int si = 0; si < 2; ++si) {
+    const GnSrc& S = si == 0 ? s0 : s1;
+    const int base = si == 0 ? 0 : s0.c;
+    // channels of this group that live in source si
+    const int lo = (ch_lo > base ? ch_lo : base) - base;
+    const int hi = (ch_hi < base + S.c ? ch_hi : base + S.c) - base;
+    if (S.c == 0 || hi <= lo) continue;
+    const int nch = hi - lo;
+    const int nq = 4 / S.bn, q0 = (n % S.bn) * nq;
+    const long long tile0 = static_cast<long long>(n / S.bn) * S.tiles_xy;
+    const int per_rep = S.tiles_xy * nq * nch;
+    const int items = S.reps * per_rep;
+    for (int it = threadIdx.x; it < items; it += 128) {
+      const int rep = it / per_rep, r = it - rep * per_rep;
+      const int ch = lo + r % nch;
+      const int bi = r / nch;
+      const long long blk = static_cast<long long>(rep) * S.m_tiles * 4 + (tile0 + bi / nq) * 4 + q0 + bi % nq;
+      const float2 e = __ldg(S.parts + blk * S.c + ch);
+      s += static_cast<double>(e.x);
+      q += static_cast<double>(e.y);
+    }
   }
   s_s[threadIdx.x] = s;
   s_q[threadIdx.x] = q;
@@ -548,17 +563,35 @@ extern "C" int sg_groupnorm_apply(const void* x0, int32_t c0, const void* x1, in
   SG_LAUNCH_END();
 }
 
-extern "C" int sg_groupnorm_finalize(const float* parts0, int32_t c0, const float* parts1, int32_t c1, int32_t n_img,
-                                     int32_t hw, int32_t tiles_xy, int32_t imgs_per_tile, int32_t groups, float eps,
-                                     float* mean_rstd, void* stream) {
-  const int C = c0 + c1;
-  if (!parts0 || !mean_rstd || (c1 > 0 && !parts1)) return SG_ERR_ARG;
-  if (C % groups || groups < 1 || tiles_xy < 1 || n_img < 1) return SG_ERR_SHAPE;
-  if (imgs_per_tile != 1 && imgs_per_tile != 2 && imgs_per_tile != 4) return SG_ERR_SHAPE;
-  if (static_cast<long long>(tiles_xy) * 128 / imgs_per_tile < hw) return SG_ERR_SHAPE;  // the quarters must cover the image
+extern "C" int sg_groupnorm_finalize(const sg_gn_parts* src0, const sg_gn_parts* src1, int32_t n_img, int32_t hw,
+                                     int32_t groups, float eps, float* mean_rstd, void* stream) {
+  if (!src0 || !src0->parts || !mean_rstd || (src1 && !src1->parts)) return SG_ERR_ARG;
+  GnSrc s[2];
+  memset(s, 0, sizeof(s));
+  const sg_gn_parts* in[2] = {src0, src1};
+  int C = 0;
+  for (int i = 0; i < 2; ++i) {
+    if (!in[i]) {
+      s[i].bn = 1;
+      continue;
+    }
+    const sg_gn_parts& p = *in[i];
+    if (p.c < 1 || p.tiles_xy < 1 || p.reps < 1 || p.m_tiles < 1) return SG_ERR_SHAPE;
+    if (p.imgs_per_tile != 1 && p.imgs_per_tile != 2 && p.imgs_per_tile != 4) return SG_ERR_SHAPE;
+    // the quarters of all reps must cover the image exactly once
+    if (static_cast<long long>(p.reps) * p.tiles_xy * 128 / p.imgs_per_tile < hw) return SG_ERR_SHAPE;
+    if (reinterpret_cast<uintptr_t>(p.parts) & 7) return SG_ERR_ALIGN;
+    s[i].parts = reinterpret_cast<const float2*>(p.parts);
+    s[i].c = p.c;
+    s[i].tiles_xy = p.tiles_xy;
+    s[i].bn = p.imgs_per_tile;
+    s[i].reps = p.reps;
+    s[i].m_tiles = p.m_tiles;
+    C += p.c;
+  }
+  if (groups < 1 || C % groups || n_img < 1) return SG_ERR_SHAPE;
   gn_finalize_kernel<<<dim3(groups, n_img), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float2*>(parts0), c0, reinterpret_cast<const float2*>(parts1), c1, hw, tiles_xy,
-      imgs_per_tile, groups, eps, reinterpret_cast<float2*>(mean_rstd));
+      s[0], s[1], hw, groups, eps, reinterpret_cast<float2*>(mean_rstd));
   SG_LAUNCH_END();
 }
 

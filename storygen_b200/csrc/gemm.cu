@@ -289,6 +289,16 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   kp.ln_inv_k = 1.0f / static_cast<float>(a->Ktot);
   kp.ln_eps = a->ln_eps;
   kp.col_stats_out = a->col_stats_out;
+  if (a->out_stride_w == 0 && a->out_stride_h == 0 && a->out_stride_n == 0) {
+    kp.osw = a->ldo;
+    kp.osh = static_cast<long long>(a->out_w) * a->ldo;
+    kp.osn = static_cast<long long>(a->out_h) * a->out_w * a->ldo;
+  } else {
+    if (a->mode == SG_EPI_NCHW_F32 || (a->out_stride_w % 8) || (a->out_stride_h % 8) || (a->out_stride_n % 8)) return SG_ERR_ALIGN;
+    kp.osw = a->out_stride_w;
+    kp.osh = a->out_stride_h;
+    kp.osn = a->out_stride_n;
+  }
 
   const int num_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n * kp.num_n_tiles;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);

@@ -43,6 +43,7 @@ struct GemmKParams {
   int ln_parts;
   float ln_inv_k, ln_eps;
   float* col_stats_out;   // [num_m_tiles * 4][N][2]
+  long long osw, osh, osn;  // output element strides of (x, y, n)  (dense: ldo, out_w * ldo, out_h * out_w * ldo)
 };
 
 template <int BN>
@@ -137,7 +138,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
   const float* lane_bias_row =
       (p.lane_bias != nullptr) ? p.lane_bias + static_cast<long long>(n) * p.ld_lane_bias : nullptr;
   // phase-B rows of this lane
-  long long mB[kIter];
+  long long mB[kIter], oB[kIter];  // row index (residual / statistics) and output element offset
   bool okB[kIter];
   if constexpr (MODE != SG_EPI_NCHW_F32) {
 #pragma unroll
@@ -146,6 +147,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
       row_coords(quarter * 32 + i * kRpi + lane / kLpr, xb, yb, nb);
       okB[i] = (xb < p.out_w) && (yb < p.out_h) && (nb < p.out_n);
       mB[i] = (static_cast<long long>(nb) * p.out_h + yb) * p.out_w + xb;
+      oB[i] = nb * p.osn + yb * p.osh + xb * p.osw;
     }
   }
   // Residual prefetch (coalesced, phase-B mapping) BEFORE the accumulator is awaited: its DRAM latency
@@ -303,8 +305,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
             fin[8 * j + 0] = a0.x; fin[8 * j + 1] = a0.y; fin[8 * j + 2] = a1.x; fin[8 * j + 3] = a1.y;
             fin[8 * j + 4] = a2.x; fin[8 * j + 5] = a2.y; fin[8 * j + 6] = a3.x; fin[8 * j + 7] = a3.y;
             if (row_ok) {
-              const long long m = (static_cast<long long>(n) * p.out_h + y) * p.out_w + x;
-              reinterpret_cast<uint4*>(p.out + m * p.ldo + col0)[j] = q;
+              reinterpret_cast<uint4*>(p.out + (n * p.osn + y * p.osh + x * p.osw) + col0)[j] = q;
             }
           }
           if (row_out) {
@@ -403,7 +404,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
               }
              }
             }
-            if (okB[i]) *reinterpret_cast<uint4*>(p.out + mB[i] * p.ldo + ocol + (lane % kLpr) * 8) = q;
+            if (okB[i]) *reinterpret_cast<uint4*>(p.out + oB[i] + ocol + (lane % kLpr) * 8) = q;
           }
           if constexpr (MODE == SG_EPI_LINEAR) {
             if (col_out) {

@@ -34,12 +34,15 @@ F32 = torch.float32
 
 
 class Act:
-    """An NHWC activation (n, h, w, c) plus, when its producer emitted them, the per-channel GroupNorm partials
-    (sg_gemm col_stats_out) of the 32-row blocks of its pixel grid."""
+    """An NHWC activation (n, h, w, c) plus, when its producer(s) emitted them, its per-channel GroupNorm partials
+    (ops.ColStats)."""
     __slots__ = ("t", "cs")
 
     def __init__(self, t, cs=None):
         self.t, self.cs = t, cs
+
+    def stats(self, i=0):
+        return None if self.cs is None else self.cs.rep(i)
 
 
 class UNetEngine:
@@ -94,6 +97,26 @@ class UNetEngine:
             b2 = b2 + r.conv_shortcut.bias.detach()
         d["w2"], d["b2"], d["shortcut"] = self._bf(w2), self._f32(b2), r.conv_shortcut is not None
         return d
+
+    def _pack_upsample(self, conv):
+        """Weights of the 4 sub-pixel phases of (nearest 2x up-sample -> conv3x3): along each axis phase 0 sees the input
+        pixels (i-1, i) with taps (k0, k1 + k2), phase 1 the pixels (i, i+1) with taps (k0 + k1, k2).  Summed in fp32,
+        rounded to bf16 once; packed [co, (ty, tx, ci)]."""
+        w = conv.weight.detach().to(self.dev, F32)  # [co, ci, ky, kx]
+        comb = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+        ws = []
+        for py in range(2):
+            for px in range(2):
+                taps = []
+                for ty in range(2):
+                    for tx in range(2):
+                        acc = 0
+                        for ky in comb[py][ty]:
+                            for kx in comb[px][tx]:
+                                acc = acc + w[:, :, ky, kx]
+                        taps.append(acc)  # [co, ci]
+                ws.append(torch.stack(taps, 1).reshape(w.shape[0], -1).to(BF16).contiguous())
+        return dict(w=ws, b=self._f32(conv.bias))
 
     def _fold_ln(self, w, b, norm, perm=None):
         """LayerNorm folded into the Linear that follows it (model/attention.py:250,268,283,298):
@@ -168,8 +191,7 @@ class UNetEngine:
             d = dict(res=[self._pack_resnet(r, tw, tb) for r in blk.resnets])
             d["attn"] = [self._pack_transformer(t) for t in blk.attentions] if blk.has_cross_attention else None
             if blk.upsamplers is not None:
-                cv = blk.upsamplers[0].conv
-                d["up"] = (self._bf(self._conv3(cv.weight)), self._f32(cv.bias))
+                d["up"] = self._pack_upsample(blk.upsamplers[0].conv)
             else:
                 d["up"] = None
             self.up.append(d)
@@ -203,9 +225,8 @@ class UNetEngine:
 
     def _new_act(self, n, h, w, c) -> Act:
         """Output buffer of a GEMM on the (w, h, n) pixel grid + the buffer for its GroupNorm partials."""
-        blocks = ops.col_stat_blocks((w, h, n))[0] if self.fuse_gn_stats else 0
-        cs = torch.empty(blocks, c, 2, dtype=F32, device=self.dev) if blocks else None
-        return Act(self._new(n, h, w, c), cs)
+        ok = self.fuse_gn_stats and ops.ColStats.layout((w, h, n)) is not None
+        return Act(self._new(n, h, w, c), ops.ColStats((w, h, n), c, self.dev) if ok else None)
 
     def _gn(self, a0: Act, a1, gamma_beta, eps, silu):
         """[SiLU](GroupNorm(concat_c(a0, a1))) -> (n, hw, c) tensor."""
@@ -216,8 +237,7 @@ class UNetEngine:
         x0 = a0.t.view(n, hw, -1)
         x1 = None if a1 is None else a1.t.view(n, hw, -1)
         if a0.cs is not None and (a1 is None or a1.cs is not None):
-            _, tiles_xy, bn = ops.col_stat_blocks((w, h, n))
-            ops.groupnorm_from_parts(x0, a0.cs, x1, None if a1 is None else a1.cs, n, hw, tiles_xy, bn, self.groups, eps,
+            ops.groupnorm_from_parts(x0, a0.cs, x1, None if a1 is None else a1.cs, n, hw, self.groups, eps,
                                      gamma_beta[0], gamma_beta[1], silu, out, self._new(n, self.groups, 2, dtype=F32))
         else:  # a producer without statistics (fewer than 32 pixels per image and tile): separate statistics pass
             ops.groupnorm(x0, x1, n, hw, self.groups, eps, gamma_beta[0], gamma_beta[1], silu, out, self._stats)
@@ -230,7 +250,7 @@ class UNetEngine:
         xn = self._gn(a0, a1, p["gn1"], self.eps, True)
         h1 = self._new_act(n, h, w, cout)
         ops.gemm([Src.nhwc(xn.view(n, h, w, -1))], taps3x3(0, p["cin"]), (w, h, n), p["w1"], h1.t,
-                 lane_bias=lane_bias[:, p["temb_off"]:], ld_lane_bias=lane_bias.shape[1], col_stats_out=h1.cs)
+                 lane_bias=lane_bias[:, p["temb_off"]:], ld_lane_bias=lane_bias.shape[1], col_stats_out=h1.stats())
         hn = self._gn(h1, None, p["gn2"], self.eps, True)
         out = self._new_act(n, h, w, cout)
         srcs = [Src.nhwc(hn.view(n, h, w, cout))]
@@ -244,7 +264,7 @@ class UNetEngine:
                 segs.append((2, 0, 0, 0, a1.t.shape[-1] // 64))
         else:
             residual = a0.t
-        ops.gemm(srcs, segs, (w, h, n), p["w2"], out.t, bias=p["b2"], residual=residual, col_stats_out=out.cs)
+        ops.gemm(srcs, segs, (w, h, n), p["w2"], out.t, bias=p["b2"], residual=residual, col_stats_out=out.stats())
         return out
 
     def project_text(self, encoder_hidden_states, out=None):
@@ -311,7 +331,7 @@ class UNetEngine:
         # follow that grid's tiling, so it runs on the pixel grid (1x1 conv form)
         out = self._new_act(n, h, w, x.shape[-1])
         ops.gemm([Src.nhwc(h3.view(n, h, w, c))], [(0, 0, 0, 0, c // 64)], (w, h, n), p["w_out"], out.t, bias=p["b_out"],
-                 residual=x.view(m, -1), col_stats_out=out.cs)
+                 residual=x.view(m, -1), col_stats_out=out.stats())
         return out, h1.view(n, hw, c)
 
     def _downsample(self, wb, xa: Act) -> Act:
@@ -322,16 +342,26 @@ class UNetEngine:
         # input row 2*oy + ky - 1: ky=0 -> odd phase shifted by -1, ky=1 -> even phase, ky=2 -> odd phase
         ph, sh = (1, 0, 1), (-1, 0, 0)
         segs = [(ph[ky] * 2 + ph[kx], sh[kx], sh[ky], 0, c // 64) for ky in range(3) for kx in range(3)]
-        ops.gemm(srcs, segs, (w // 2, h // 2, n), wb[0], out.t, bias=wb[1], col_stats_out=out.cs)
+        ops.gemm(srcs, segs, (w // 2, h // 2, n), wb[0], out.t, bias=wb[1], col_stats_out=out.stats())
         return out
 
-    def _upsample(self, wb, xa: Act) -> Act:
+    def _upsample(self, wp, xa: Act) -> Act:
+        """Upsample2D (model/unet_2d_blocks.py:581-584: nearest 2x, then conv3x3) as four 2x2-tap convolutions of the
+        LOW-resolution tensor, one per output sub-pixel phase (py, px), with the 3x3 taps that fall on the same input
+        pixel pre-summed (_pack_upsample): 4/9 of the FLOPs, the up-sampled tensor is never materialised, and every
+        phase writes every second pixel of the output through the GEMM's strided store."""
         x = xa.t
         n, h, w, c = x.shape
-        up = self._new(n, 2 * h, 2 * w, c)
-        ops.upsample2x(x, up)
-        out = self._new_act(n, 2 * h, 2 * w, c)
-        ops.gemm([Src.nhwc(up)], taps3x3(0, c), (2 * w, 2 * h, n), wb[0], out.t, bias=wb[1], col_stats_out=out.cs)
+        H, W = 2 * h, 2 * w
+        ok = self.fuse_gn_stats and ops.ColStats.layout((w, h, n)) is not None
+        out = Act(self._new(n, H, W, c), ops.ColStats((w, h, n), c, self.dev, reps=4) if ok else None)
+        for py in range(2):
+            for px in range(2):
+                # phase 0 reads input rows (y-1, y), phase 1 rows (y, y+1); same along x
+                segs = [(0, px - 1 + tx, py - 1 + ty, 0, c // 64) for ty in range(2) for tx in range(2)]
+                ops.gemm([Src.nhwc(x)], segs, (w, h, n), wp["w"][py * 2 + px], out.t, bias=wp["b"],
+                         col_stats_out=out.stats(py * 2 + px), out_strides=(2 * c, 2 * W * c, H * W * c),
+                         out_offset=(py * W + px) * c)
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -413,7 +443,7 @@ class UNetEngine:
         # conv_in as a K = 64 GEMM over the pre-gathered patches, on the pixel grid (so that its GroupNorm partials
         # follow the grid's tiling)
         ops.gemm([Src.nhwc(patches.view(n, h, w, 64))], [(0, 0, 0, 0, 1)], (w, h, n), self.conv_in[0], x.t,
-                 bias=self.conv_in[1], col_stats_out=x.cs)
+                 bias=self.conv_in[1], col_stats_out=x.stats())
         skips = [x]
         hh, ww = h, w
         for i, blk in enumerate(self.down):

@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import SG_EPI_GEGLU, SG_EPI_LINEAR, SG_EPI_NCHW_F32, SgAttnArgs, SgGemmArgs
+from ._lib import SG_EPI_GEGLU, SG_EPI_LINEAR, SG_EPI_NCHW_F32, SgAttnArgs, SgGemmArgs, SgGnParts
 
 BF16 = torch.bfloat16
 TRACE = None  # set to a list to record (kernel, shape...) of every launch, in order (profiling aid)
@@ -90,28 +90,49 @@ def row_stat_parts(grid: Tuple[int, int, int], n_cols: int) -> int:
     return v
 
 
-def col_stat_blocks(grid: Tuple[int, int, int]) -> Tuple[int, int, int]:
-    """(number of 32-row blocks, tiles_xy, imgs_per_tile) of the per-channel statistics a GEMM on this output grid
-    writes (sg_gemm col_stats_out), or (0, 0, 0) when a 32-row quarter would span two images (fewer than 32 pixels per
-    image and tile: the consumer then falls back to sg_groupnorm_stats)."""
-    w, h, n = grid
-    bw, bh, bn = tile_box(w, h, n)
-    if (bw * bh) % 32 != 0 or bn > 4:
-        return 0, 0, 0
-    tx, ty, tn = -(-w // bw), -(-h // bh), -(-n // bn)
-    return tx * ty * tn * 4, tx * ty, bn
+class ColStats:
+    """Per-channel GroupNorm partials of a tensor, as written by the `reps` GEMMs that produced it on the (w, h, n) pixel
+    grid (sg_gemm col_stats_out; reps = 4 for the sub-pixel phases of an up-sampling conv).  buf: fp32 (reps, blocks, c, 2)."""
+    __slots__ = ("buf", "c", "tiles_xy", "bn", "reps", "m_tiles")
+
+    @staticmethod
+    def layout(grid: Tuple[int, int, int]):
+        """(m_tiles, tiles_xy, imgs_per_tile) or None when a 32-row quarter would span two images (fewer than 32 pixels
+        per image and tile: the consumer then falls back to the separate statistics pass, sg_groupnorm_stats)."""
+        w, h, n = grid
+        bw, bh, bn = tile_box(w, h, n)
+        if (bw * bh) % 32 != 0 or bn > 4:
+            return None
+        tx, ty, tn = -(-w // bw), -(-h // bh), -(-n // bn)
+        return tx * ty * tn, tx * ty, bn
+
+    def __init__(self, grid: Tuple[int, int, int], c: int, device, reps: int = 1):
+        self.m_tiles, self.tiles_xy, self.bn = ColStats.layout(grid)
+        self.c, self.reps = c, reps
+        self.buf = torch.empty(reps, self.m_tiles * 4, c, 2, dtype=torch.float32, device=device)
+
+    def rep(self, i: int) -> torch.Tensor:
+        return self.buf[i]
+
+    def desc(self) -> SgGnParts:
+        d = SgGnParts()
+        d.parts, d.c, d.tiles_xy, d.imgs_per_tile, d.reps, d.m_tiles = self.buf.data_ptr(), self.c, self.tiles_xy, self.bn, self.reps, self.m_tiles
+        return d
 
 
 def gemm(srcs: Sequence[Src], segs: Sequence[Tuple[int, int, int, int, int]], grid: Tuple[int, int, int],
          weight: torch.Tensor, out: torch.Tensor, bias: Optional[torch.Tensor] = None,
          lane_bias: Optional[torch.Tensor] = None, ld_lane_bias: int = 0, residual: Optional[torch.Tensor] = None,
          res_scale: float = 1.0, mode: int = SG_EPI_LINEAR, out_channels: int = 0,
-         row_stats_out: Optional[torch.Tensor] = None, ln=None, col_stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         row_stats_out: Optional[torch.Tensor] = None, ln=None, col_stats_out: Optional[torch.Tensor] = None,
+         out_strides: Optional[Tuple[int, int, int]] = None, out_offset: int = 0) -> torch.Tensor:
     """out[m, :] = epilogue(sum_k A[m, k] W[:, k]); see include/storygen_b200.h (sg_gemm).
     segs: (src, dx, dy, c0, nkb); grid: (out_w, out_h, out_n); weight: bf16 [N, Ktot].
     row_stats_out: fp32 (row_stat_parts(grid, N), M, 2) receiving the output's per-row LayerNorm partials;
     ln = (stats (parts, M, 2), csum (N,), eps): apply LayerNorm of the A rows in the epilogue (weight pre-scaled by gamma);
-    col_stats_out: fp32 (col_stat_blocks(grid)[0], N, 2) receiving the output's per-channel GroupNorm partials."""
+    col_stats_out: fp32 (4 * M tiles, N, 2) receiving the output's per-channel GroupNorm partials (ColStats.rep(i));
+    out_strides / out_offset: element strides of (x, y, n) and first element when the output pixels are a strided
+    sub-grid of `out` (sub-pixel phase of an up-sampling conv)."""
     a = SgGemmArgs()
     a.num_src = len(srcs)
     for i, s in enumerate(srcs):
@@ -136,8 +157,10 @@ def gemm(srcs: Sequence[Src], segs: Sequence[Tuple[int, int, int, int, int]], gr
     a.ld_lane_bias = ld_lane_bias
     a.residual = _ptr(residual)
     a.ldr = residual.shape[-1] if residual is not None else 0
-    a.out = out.data_ptr()
+    a.out = out.data_ptr() + out_offset * out.element_size()
     a.ldo = out.shape[-1]
+    if out_strides is not None:
+        a.out_stride_w, a.out_stride_h, a.out_stride_n = out_strides
     if row_stats_out is not None:
         _req(row_stats_out, torch.float32, "row_stats_out")
         a.row_stats_out = row_stats_out.data_ptr()
@@ -205,16 +228,18 @@ def groupnorm(x0: torch.Tensor, x1: Optional[torch.Tensor], n: int, hw: int, gro
     return out
 
 
-def groupnorm_from_parts(x0: torch.Tensor, parts0: torch.Tensor, x1: Optional[torch.Tensor], parts1: Optional[torch.Tensor],
-                         n: int, hw: int, tiles_xy: int, imgs_per_tile: int, groups: int, eps: float, gamma: torch.Tensor,
-                         beta: torch.Tensor, silu: bool, out: torch.Tensor, mean_rstd: torch.Tensor):
+def groupnorm_from_parts(x0: torch.Tensor, st0: ColStats, x1: Optional[torch.Tensor], st1: Optional[ColStats], n: int, hw: int,
+                         groups: int, eps: float, gamma: torch.Tensor, beta: torch.Tensor, silu: bool, out: torch.Tensor,
+                         mean_rstd: torch.Tensor):
     """y = [SiLU](GroupNorm(concat_c(x0, x1))) with the statistics the PRODUCING GEMMs emitted (col_stats_out): one tiny
     reduction kernel (fixed order, fp64) + the apply pass; no pass over the activations for the statistics."""
     lib = _lib.load()
     c0 = x0.shape[-1]
     c1 = x1.shape[-1] if x1 is not None else 0
-    _lib.check(lib.sg_groupnorm_finalize(parts0.data_ptr(), c0, _ptr(parts1), c1, n, hw, tiles_xy, imgs_per_tile, groups,
-                                         eps, mean_rstd.data_ptr(), _stream()), "sg_groupnorm_finalize")
+    d0 = st0.desc()
+    d1 = st1.desc() if st1 is not None else None
+    _lib.check(lib.sg_groupnorm_finalize(C.byref(d0), C.byref(d1) if d1 is not None else None, n, hw, groups, eps,
+                                         mean_rstd.data_ptr(), _stream()), "sg_groupnorm_finalize")
     _lib.check(lib.sg_groupnorm_apply_ms(x0.data_ptr(), c0, _ptr(x1), c1, n, hw, groups, mean_rstd.data_ptr(),
                                          gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(), _stream()),
                "sg_groupnorm_apply_ms")

@@ -308,20 +308,19 @@ def test_groupnorm_from_producer_statistics(n, h, w, c0, c1, offset):
     1x1 conv: transposed epilogue), against torch.group_norm of the bf16 tensors.  offset: |mean| >> std (the fp64
     finalisation must not cancel)."""
     groups, hw = 32, h * w
-    blocks, tiles_xy, bn = ops.col_stat_blocks((w, h, n))
-    assert blocks > 0
+    assert ops.ColStats.layout((w, h, n)) is not None
 
     def produce(c, k, seed, conv3):
         a = rnd(n, h, w, k, seed=seed)
         bias = (rnd(c, seed=seed + 1, dtype=torch.float32) + offset).contiguous()
         out = torch.empty(n, h, w, c, dtype=BF16, device=DEV)
-        cs = torch.empty(blocks, c, 2, dtype=torch.float32, device=DEV)
+        cs = ops.ColStats((w, h, n), c, DEV)
         if conv3:
             wt = rnd(c, 9 * k, scale=(9 * k) ** -0.5, seed=seed + 2)
-            ops.gemm([Src.nhwc(a)], taps3x3(0, k), (w, h, n), wt, out, bias=bias, col_stats_out=cs)
+            ops.gemm([Src.nhwc(a)], taps3x3(0, k), (w, h, n), wt, out, bias=bias, col_stats_out=cs.rep(0))
         else:
             wt = rnd(c, k, scale=k ** -0.5, seed=seed + 2)
-            ops.gemm([Src.nhwc(a)], [(0, 0, 0, 0, k // 64)], (w, h, n), wt, out, bias=bias, col_stats_out=cs)
+            ops.gemm([Src.nhwc(a)], [(0, 0, 0, 0, k // 64)], (w, h, n), wt, out, bias=bias, col_stats_out=cs.rep(0))
         return out, cs
 
     x0, cs0 = produce(c0, 320, 10, True)
@@ -330,8 +329,39 @@ def test_groupnorm_from_producer_statistics(n, h, w, c0, c1, offset):
     gamma, beta = rnd(c, seed=5, dtype=torch.float32) * 0.2 + 1.0, rnd(c, seed=6, dtype=torch.float32) * 0.1
     out = torch.empty(n, hw, c, dtype=BF16, device=DEV)
     mr = torch.empty(n, groups, 2, dtype=torch.float32, device=DEV)
-    ops.groupnorm_from_parts(x0.view(n, hw, c0), cs0, None if x1 is None else x1.view(n, hw, c1), cs1, n, hw, tiles_xy, bn,
-                             groups, 1e-5, gamma, beta, True, out, mr)
+    ops.groupnorm_from_parts(x0.view(n, hw, c0), cs0, None if x1 is None else x1.view(n, hw, c1), cs1, n, hw, groups, 1e-5,
+                             gamma, beta, True, out, mr)
     xcat = x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], -1)
     ref = F.silu(F.group_norm(xcat.permute(0, 3, 1, 2), groups, gamma, beta, 1e-5)).permute(0, 2, 3, 1).reshape(n, hw, c)
     close(out, ref, rel=0.015, abs_=0.03)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 8, 8, 128), (3, 16, 16, 320), (1, 32, 32, 64)])
+def test_upsample_conv_as_four_subpixel_phases(n, h, w, c):
+    """Upsample2D (nearest 2x -> conv3x3) as four 2x2-tap convolutions of the low-resolution tensor with pre-summed
+    weights and a strided store (engine._upsample / _pack_upsample), + GroupNorm of the result from the four phases'
+    statistics, against F.interpolate + F.conv2d + F.group_norm."""
+    g = torch.Generator("cpu").manual_seed(3)
+    x = torch.randn(n, h, w, c, generator=g).to(BF16).to(DEV)
+    wt = (torch.randn(c, c, 3, 3, generator=g) * (9 * c) ** -0.5).to(DEV)
+    b = (torch.randn(c, generator=g) * 0.1).to(DEV)
+    comb = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    H, W = 2 * h, 2 * w
+    out = torch.zeros(n, H, W, c, dtype=BF16, device=DEV)
+    cs = ops.ColStats((w, h, n), c, DEV, reps=4)
+    for py in range(2):
+        for px in range(2):
+            taps = [sum(wt[:, :, ky, kx] for ky in comb[py][ty] for kx in comb[px][tx]) for ty in range(2) for tx in range(2)]
+            wp = torch.stack(taps, 1).reshape(c, -1).to(BF16).contiguous()
+            segs = [(0, px - 1 + tx, py - 1 + ty, 0, c // 64) for ty in range(2) for tx in range(2)]
+            ops.gemm([Src.nhwc(x)], segs, (w, h, n), wp, out, bias=b, col_stats_out=cs.rep(py * 2 + px),
+                     out_strides=(2 * c, 2 * W * c, H * W * c), out_offset=(py * W + px) * c)
+    xin = x.float().permute(0, 3, 1, 2)
+    ref = F.conv2d(F.interpolate(xin, scale_factor=2.0, mode="nearest"), wt, b, padding=1)
+    close(out.permute(0, 3, 1, 2), ref, rel=0.012, abs_=0.03)
+    gamma, beta = rnd(c, seed=5, dtype=torch.float32) * 0.2 + 1.0, rnd(c, seed=6, dtype=torch.float32) * 0.1
+    y = torch.empty(n, H * W, c, dtype=BF16, device=DEV)
+    mr = torch.empty(n, 32, 2, dtype=torch.float32, device=DEV)
+    ops.groupnorm_from_parts(out.view(n, H * W, c), cs, None, None, n, H * W, 32, 1e-5, gamma, beta, False, y, mr)
+    refn = F.group_norm(out.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5).permute(0, 2, 3, 1).reshape(n, H * W, c)
+    close(y, refn, rel=0.015, abs_=0.03)
