@@ -6,9 +6,10 @@
 //                                two accumulator stages so the epilogue of tile i overlaps tile i+1)
 //   warps 2..9  : epilogue      two warpgroups, each thread owns one accumulator row; the 32-column chunks
 //                               of a tile alternate between the groups (2 warps per SM sub-partition hide
-//                               each other's TMEM / global latency); residual row segments are prefetched
-//                               into registers before the accumulator is awaited
-//                               (tcgen05.ld -> bias / time-embedding / residual / GEGLU -> bf16 stores)
+//                               each other's latency); residual rows, bias vectors and LayerNorm statistics are
+//                               fetched before the accumulator is awaited; tcgen05.ld (double-buffered) ->
+//                               LN correction / bias / time-embedding / residual / GEGLU / statistics in registers
+//                               -> swizzled smem slab -> one TMA bulk store per 32-row x 32-column chunk
 //
 // Tile = 128 output pixels (a bw x bh x bn box of the NHWC output grid) x BN output channels.
 // K loop = list of segments (source tensor, dx, dy, first channel, #64-channel blocks): this one
@@ -136,11 +137,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     int acc = 0;
     uint32_t acc_phase = 0;
     int tile_ord = 0;
+    EpiState est;
+    if (lane == 0) tma_prefetch_desc(&p.out_map);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.num_n_tiles;
       const int nt = tile - mt * p.num_n_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_tile<BN, MODE>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase, tile_ord, warp);
+      epilogue_tile<BN, MODE>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase, est, tile_ord, warp);
       ++tile_ord;
       tc_fence_before();
       __syncwarp();
@@ -150,6 +153,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         acc_phase ^= 1;
       }
     }
+    // the staging slabs must outlive the TMA stores that read them
+    if (lane == 0) bulk_wait_group_read<0>();
   }
 
   tc_fence_before();
@@ -188,6 +193,9 @@ static int launch_gemm(const GemmKParams& kp, int num_tiles, cudaStream_t stream
 // the tile count would leave more than half of the SMs idle, halve the tile width until the grid fills them.
 static int pick_bn_tile(const sg_gemm_args* a) {
   int bn_tile = (a->N % 256 == 0 || a->N >= 512) ? 256 : ((a->N % 160 == 0) ? 160 : ((a->N % 128 == 0) ? 128 : 64));
+  // small K: the epilogue, not the main loop, bounds the tile; 160-wide tiles keep two staging slabs per epilogue warp
+  // (the TMA store of one chunk drains while the next is computed) and halve the accumulator a warp walks per tile
+  if (a->Ktot <= 1280 && a->N % 160 == 0 && a->mode == SG_EPI_LINEAR) bn_tile = 160;
   const long long m_tiles = static_cast<long long>((a->out_w + a->bw - 1) / a->bw) * ((a->out_h + a->bh - 1) / a->bh) *
                             ((a->out_n + a->bn - 1) / a->bn);
   while (bn_tile > 64 && bn_tile % 128 == 0 && m_tiles * ((a->N + bn_tile - 1) / bn_tile) * 2 <= num_sms()) bn_tile /= 2;
@@ -270,7 +278,27 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   kp.num_n_tiles = static_cast<int>((a->N + bn_tile - 1) / bn_tile);
   kp.N = static_cast<int>(a->N);
   kp.mode = a->mode;
-  kp.transpose_epi = (a->mode != SG_EPI_LINEAR) || (total_kb <= 24);
+  if (a->mode != SG_EPI_NCHW_F32) {
+    // output view for the epilogue's TMA stores: (column, x, y, n), one box = 32 rows (a warp's slab of the tile:
+    // sx x sy x sn pixels) x 32 (GEGLU: 16) columns, swizzle matching the slab's row pitch
+    const int out_cols = (a->mode == SG_EPI_GEGLU) ? static_cast<int>(a->N / 2) : static_cast<int>(a->N);
+    const long long osw = (a->out_stride_w || a->out_stride_h || a->out_stride_n) ? a->out_stride_w : a->ldo;
+    const long long osh = (a->out_stride_w || a->out_stride_h || a->out_stride_n) ? a->out_stride_h : static_cast<long long>(a->out_w) * a->ldo;
+    const long long osn = (a->out_stride_w || a->out_stride_h || a->out_stride_n) ? a->out_stride_n
+                                                                                 : static_cast<long long>(a->out_h) * a->out_w * a->ldo;
+    if ((osw % 8) || (osh % 8) || (osn % 8)) return SG_ERR_ALIGN;
+    const int sx = a->bw < 32 ? a->bw : 32;
+    const int sy = (a->bh < 32 / sx) ? a->bh : 32 / sx;
+    const int sn = 32 / (sx * sy);
+    uint64_t dims[4] = {static_cast<uint64_t>(out_cols), static_cast<uint64_t>(a->out_w), static_cast<uint64_t>(a->out_h),
+                        static_cast<uint64_t>(a->out_n)};
+    uint64_t strides[3] = {static_cast<uint64_t>(osw) * 2, static_cast<uint64_t>(osh) * 2, static_cast<uint64_t>(osn) * 2};
+    uint32_t box[4] = {a->mode == SG_EPI_GEGLU ? 16u : 32u, static_cast<uint32_t>(sx), static_cast<uint32_t>(sy),
+                       static_cast<uint32_t>(sn)};
+    int rc = encode_tmap_bf16(&kp.out_map, a->out, 4, dims, strides, box,
+                              a->mode == SG_EPI_GEGLU ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc != 0) return rc;
+  }
   kp.out_channels = a->out_channels;
   kp.res_scale = a->res_scale;
   kp.bias = a->bias;
@@ -289,16 +317,6 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   kp.ln_inv_k = 1.0f / static_cast<float>(a->Ktot);
   kp.ln_eps = a->ln_eps;
   kp.col_stats_out = a->col_stats_out;
-  if (a->out_stride_w == 0 && a->out_stride_h == 0 && a->out_stride_n == 0) {
-    kp.osw = a->ldo;
-    kp.osh = static_cast<long long>(a->out_w) * a->ldo;
-    kp.osn = static_cast<long long>(a->out_h) * a->out_w * a->ldo;
-  } else {
-    if (a->mode == SG_EPI_NCHW_F32 || (a->out_stride_w % 8) || (a->out_stride_h % 8) || (a->out_stride_n % 8)) return SG_ERR_ALIGN;
-    kp.osw = a->out_stride_w;
-    kp.osh = a->out_stride_h;
-    kp.osn = a->out_stride_n;
-  }
 
   const int num_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n * kp.num_n_tiles;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
