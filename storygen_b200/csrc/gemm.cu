@@ -19,10 +19,10 @@
 
 namespace sg {
 
-template <int BN, int MODE>
+template <int BN, int MODE, int RT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_kernel(const __grid_constant__ GemmKParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, RT>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   uint64_t* empty_bar = bars + Cfg::kStages;      // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;             // [kEpiWarps] residual slabs landed (RT = 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kEpiWarps);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // broadcast: the compiler treats it as warp-uniform
   const int lane = threadIdx.x & 31;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kEpiWarps);  // one arrive per epilogue warp
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -138,12 +140,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     uint32_t acc_phase = 0;
     int tile_ord = 0;
     EpiState est;
-    if (lane == 0) tma_prefetch_desc(&p.out_map);
+    if (lane == 0) {
+      tma_prefetch_desc(&p.out_map);
+      if (RT == 1) tma_prefetch_desc(&p.res_map);
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / p.num_n_tiles;
       const int nt = tile - mt * p.num_n_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_tile<BN, MODE>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase, est, tile_ord, warp);
+      epilogue_tile<BN, MODE, RT>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase, est,
+                                  &res_bar[warp - 2], tile_ord, warp);
       ++tile_ord;
       tc_fence_before();
       __syncwarp();
@@ -165,19 +171,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int RT = 0>
 static int launch_gemm_mode(const GemmKParams& kp, int num_tiles, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, RT>;
   static std::atomic<uint64_t> configured{0};
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<BN, MODE>), Cfg::kSmemBytes, &configured)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<BN, MODE, RT>), Cfg::kSmemBytes, &configured)) return rc;
   int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_kernel<BN, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
+  gemm_kernel<BN, MODE, RT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
 template <int BN>
-static int launch_gemm(const GemmKParams& kp, int num_tiles, cudaStream_t stream) {
+static int launch_gemm(const GemmKParams& kp, int num_tiles, bool res_tma, cudaStream_t stream) {
+  if constexpr (BN <= 160) {
+    if (res_tma && kp.mode == SG_EPI_LINEAR) return launch_gemm_mode<BN, SG_EPI_LINEAR, 1>(kp, num_tiles, stream);
+  }
   switch (kp.mode) {
     case SG_EPI_GEGLU: return launch_gemm_mode<BN, SG_EPI_GEGLU>(kp, num_tiles, stream);
     case SG_EPI_NCHW_F32:
@@ -278,6 +287,7 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   kp.num_n_tiles = static_cast<int>((a->N + bn_tile - 1) / bn_tile);
   kp.N = static_cast<int>(a->N);
   kp.mode = a->mode;
+  bool res_tma = false;
   if (a->mode != SG_EPI_NCHW_F32) {
     // output view for the epilogue's TMA stores: (column, x, y, n), one box = 32 rows (a warp's slab of the tile:
     // sx x sy x sn pixels) x 32 (GEGLU: 16) columns, swizzle matching the slab's row pitch
@@ -298,6 +308,17 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
     int rc = encode_tmap_bf16(&kp.out_map, a->out, 4, dims, strides, box,
                               a->mode == SG_EPI_GEGLU ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc != 0) return rc;
+    // small-K GEMMs with a residual (the transformer blocks' out-projections and proj_out): their epilogue is the critical
+    // path, so the residual comes in through TMA slabs instead of row-per-thread global reads
+    res_tma = (a->mode == SG_EPI_LINEAR) && (a->residual != nullptr) && (a->Ktot <= 1280) && (bn_tile <= 160);
+    if (res_tma) {
+      uint64_t rdims[4] = {static_cast<uint64_t>(a->N), static_cast<uint64_t>(a->out_w), static_cast<uint64_t>(a->out_h),
+                           static_cast<uint64_t>(a->out_n)};
+      uint64_t rstrides[3] = {static_cast<uint64_t>(a->ldr) * 2, static_cast<uint64_t>(a->out_w) * a->ldr * 2,
+                              static_cast<uint64_t>(a->out_h) * a->out_w * a->ldr * 2};
+      rc = encode_tmap_bf16(&kp.res_map, a->residual, 4, rdims, rstrides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != 0) return rc;
+    }
   }
   kp.out_channels = a->out_channels;
   kp.res_scale = a->res_scale;
@@ -321,9 +342,9 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   const int num_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n * kp.num_n_tiles;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   switch (bn_tile) {
-    case 256: return launch_gemm<256>(kp, num_tiles, stream);
-    case 160: return launch_gemm<160>(kp, num_tiles, stream);
-    case 128: return launch_gemm<128>(kp, num_tiles, stream);
-    default: return launch_gemm<64>(kp, num_tiles, stream);
+    case 256: return launch_gemm<256>(kp, num_tiles, false, stream);
+    case 160: return launch_gemm<160>(kp, num_tiles, res_tma, stream);
+    case 128: return launch_gemm<128>(kp, num_tiles, res_tma, stream);
+    default: return launch_gemm<64>(kp, num_tiles, res_tma, stream);
   }
 }

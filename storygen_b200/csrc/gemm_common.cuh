@@ -15,6 +15,7 @@ struct GemmKParams {
   CUtensorMap a_maps[SG_MAX_SRC];
   CUtensorMap b_map;
   CUtensorMap out_map;  // (col, x, y, n) view of the output, box = (32 | 16 columns) x (one warp's 32-row slab of the tile)
+  CUtensorMap res_map;  // same view of the residual (RT = 1 kernels: residual slabs fetched by TMA)
   sg_seg segs[SG_MAX_SEGS];
   int num_segs;
   int total_kb;
@@ -45,22 +46,30 @@ struct GemmKParams {
   float* col_stats_out;   // [num_m_tiles * 4][N][2]
 };
 
-// Per epilogue warp: kStageBufs staging buffers of [32 rows x 64 B] (the TMA store's source) + the bias / csum vectors
-// of the warp's (at most 4) 32-column chunks of a tile.
-template <int BN>
+// Per epilogue warp: kSlabs staging slabs of [32 rows x 64 B] (the TMA store's source) + the bias / csum vectors of the
+// warp's (at most 4) 32-column chunks of a tile.
+//   RT = 0: 2 slabs used alternately (1 for 256-wide tiles, whose deep operand ring needs the shared memory); a
+//           residual is read by the threads themselves, row by row (fine when the main loop hides the epilogue);
+//   RT = 1: one slab per chunk of the tile; the residual's slabs are fetched INTO them by TMA at the start of the tile,
+//           every thread adds its row in place and the same slab is the TMA store's source.  For the small-K GEMMs of
+//           the transformer blocks (K = C or 2C), whose epilogue is the critical path: a row-per-thread global read costs
+//           one L1 wavefront per 16 bytes, the bulk copy none.
+template <int BN, int RT = 0>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStageBufs = (BN == 256) ? 1 : 2;
+  static constexpr int kMine = (BN / 32 + 1) / 2;  // chunks of a tile per epilogue warp
+  static constexpr int kSlabs = RT ? kMine : ((BN == 256) ? 1 : 2);
   static constexpr int kVecBytes = 2 * 4 * 128;  // bias[4][32] + csum[4][32] floats
-  static constexpr int kWarpScratch = kStageBufs * 2048 + kVecBytes;
+  static constexpr int kWarpScratch = kSlabs * 2048 + kVecBytes;
   static constexpr int kScratchBytes = kEpiWarps * kWarpScratch;
+  static constexpr int kBarBytes = 256;   // 2 x kStages + 4 pipeline barriers, 8 residual barriers, the TMEM slot
   static constexpr int kMaxSmem = 231424;  // 227 KB - 1 KB (reserved)
-  static constexpr int kFit = (kMaxSmem - 1024 /*align*/ - 128 /*barriers*/ - kScratchBytes) / kStageBytes;
+  static constexpr int kFit = (kMaxSmem - 1024 /*align*/ - kBarBytes - kScratchBytes) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kTmemCols = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align*/ + 128 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kScratchBytes + 1024 /*align*/ + kBarBytes;
   static_assert(kStages >= 3, "too few pipeline stages");
   static_assert(kSmemBytes <= kMaxSmem, "exceeds the 227 KB - 1 KB (reserved) dynamic shared memory limit");
 };
@@ -85,6 +94,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // still be reading the other one).
 struct EpiState {
   uint32_t store_seq = 0;
+  uint32_t res_phase = 0;  // RT = 1: parity of this warp's residual barrier
 };
 
 // One output tile of the epilogue, executed by one epilogue warp (quarter = TMEM lane quarter it may access = rows
@@ -100,12 +110,13 @@ struct EpiState {
 // are column sums of that same slab.  Before the accumulator is awaited the warp has already fetched its residual row
 // segments, the bias / csum vectors of all its chunks and its row's LayerNorm statistics, so their latency overlaps
 // the tile's main loop; TMEM loads are double-buffered.
-template <int BN, int MODE>
+template <int BN, int MODE, int RT>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt, const int nt, const uint32_t t_row,
                                               uint8_t* scratch, const int quarter, const int grp, const int lane,
-                                              uint64_t* tfull, const uint32_t tfull_phase, EpiState& st,
+                                              uint64_t* tfull, const uint32_t tfull_phase, EpiState& st, uint64_t* res_bar,
                                               const int tile_ord = 0, const int warp_id = 0) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, RT>;
+  static_assert(RT == 0 || MODE == SG_EPI_LINEAR, "TMA residual slabs: LINEAR epilogue only");
   const bool dbg_on = (p.dbg != nullptr) && blockIdx.x == 0 && lane == 0 && tile_ord < 8;
 #define SG_GT(slot) do { if (dbg_on) p.dbg[(warp_id * 8 + tile_ord) * 8 + (slot)] = clock64(); } while (0)
   SG_GT(0);
@@ -121,7 +132,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
   const bool row_ok = (x < p.out_w) && (y < p.out_h) && (n < p.out_n);
   const long long m = (static_cast<long long>(n) * p.out_h + y) * p.out_w + x;  // output row index
   const uint32_t scratch_u32 = smem_u32(scratch);
-  const uint32_t bias_u32 = scratch_u32 + Cfg::kStageBufs * 2048;
+  const uint32_t bias_u32 = scratch_u32 + Cfg::kSlabs * 2048;
   const uint32_t csum_u32 = bias_u32 + 4 * 128;
   const float* lane_bias_row =
       (p.lane_bias != nullptr) ? p.lane_bias + static_cast<long long>(n) * p.ld_lane_bias : nullptr;
@@ -130,9 +141,35 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
   const bool row_out = (MODE == SG_EPI_LINEAR) && (p.row_stats_out != nullptr);
   const bool col_out = (MODE == SG_EPI_LINEAR) && (p.col_stats_out != nullptr);
 
+  // slab of this warp inside the tile box: rows [32 quarter, +32) = sx x sy x sn pixels starting at (x0, y0, n0)
+  const int r0 = quarter * 32;
+  const int slab_x = tx * p.bw + (r0 & (p.bw - 1));
+  const int slab_y = ty * p.bh + ((r0 >> p.bw_log2) & (p.bh - 1));
+  const int slab_n = tn * p.bn + (r0 >> (p.bw_log2 + p.bh_log2));
+
   // ---- before the accumulator is awaited: everything that comes from global memory -------------------------------
-  uint4 res[(MODE == SG_EPI_LINEAR) ? kMine : 1][4];
-  if constexpr (MODE == SG_EPI_LINEAR) {
+  uint4 res[(MODE == SG_EPI_LINEAR && RT == 0) ? kMine : 1][4];
+  if constexpr (RT == 1) {
+    __syncwarp();  // every lane is done with the previous tile's slabs (column statistics read them)
+    // residual slabs by TMA into the slabs the output will leave from; slab ci is free once the store that read it in the
+    // previous tile is done (stores retire in order: wait for all but the kMine - 1 - ci youngest)
+    if (use_res && lane == 0) {
+      int nvalid = 0;
+#pragma unroll
+      for (int ci = 0; ci < kMine; ++ci)
+        if (grp + 2 * ci < kChunks && nt * BN + (grp + 2 * ci) * 32 < p.N) ++nvalid;
+      mbar_arrive_expect_tx(res_bar, static_cast<uint32_t>(nvalid) * 2048u);
+#pragma unroll
+      for (int ci = 0; ci < kMine; ++ci) {
+        const int col0 = nt * BN + (grp + 2 * ci) * 32;
+        if (grp + 2 * ci < kChunks && col0 < p.N) {
+          bulk_wait_group_read_n(kMine - 1 - ci);
+          tma_load_4d(reinterpret_cast<void*>(scratch + ci * 2048), &p.res_map, res_bar, col0, slab_x, slab_y, slab_n);
+        }
+      }
+    }
+  }
+  if constexpr (MODE == SG_EPI_LINEAR && RT == 0) {
     if (use_res && row_ok) {
 #pragma unroll
       for (int ci = 0; ci < kMine; ++ci) {
@@ -167,11 +204,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
   }
   __syncwarp();
   float rs_acc = 0.f, rq_acc = 0.f;  // per-row (sum, sumsq) of this warp's columns of the output
-  // slab of this warp inside the tile box: rows [32 quarter, +32) = sx x sy x sn pixels starting at (x0, y0, n0)
-  const int r0 = quarter * 32;
-  const int slab_x = tx * p.bw + (r0 & (p.bw - 1));
-  const int slab_y = ty * p.bh + ((r0 >> p.bw_log2) & (p.bh - 1));
-  const int slab_n = tn * p.bn + (r0 >> (p.bw_log2 + p.bh_log2));
+  bool res_waited = false;
 
   SG_GT(1);
   mbar_wait(tfull, tfull_phase);
@@ -248,14 +281,37 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
             // ops under autocast; the row statistics are taken from the fp32 value just before the final rounding
 #pragma unroll
             for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+            [[maybe_unused]] uint32_t rw[16];
+            if constexpr (RT == 1) {
+              if (use_res) {
+                // this row of the residual slab (TMA wrote it with the store's swizzle)
+                if (!res_waited) {
+                  mbar_wait(res_bar, st.res_phase);
+                  res_waited = true;
+                }
+                const uint32_t rrow = scratch_u32 + ci * 2048 + lane * 64;
+                const int sw = (lane >> 1) & 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 q = lds128(rrow + ((j ^ sw) << 4));
+                  rw[4 * j] = q.x; rw[4 * j + 1] = q.y; rw[4 * j + 2] = q.z; rw[4 * j + 3] = q.w;
+                }
+              }
+            } else {
+              if (use_res) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint4 q = res[ci][j];
+                  rw[4 * j] = q.x; rw[4 * j + 1] = q.y; rw[4 * j + 2] = q.z; rw[4 * j + 3] = q.w;
+                }
+              }
+            }
             if (use_res || row_out) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 float2 a = unpack_bf16x2(w[j]);
                 if (use_res) {
-                  const uint4 rq = res[ci][j >> 2];
-                  const uint32_t rw = (j & 3) == 0 ? rq.x : ((j & 3) == 1 ? rq.y : ((j & 3) == 2 ? rq.z : rq.w));
-                  const float2 rr = unpack_bf16x2(rw);
+                  const float2 rr = unpack_bf16x2(rw[j]);
                   a.x = fmaf(p.res_scale, rr.x, a.x);
                   a.y = fmaf(p.res_scale, rr.y, a.y);
                   w[j] = pack_bf16x2(a.x, a.y);
@@ -272,10 +328,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
             }
           }
           // ---- staging slab: [32 rows x 64 B] swizzle-64B (LINEAR) / [32 rows x 32 B] swizzle-32B (GEGLU)
-          const uint32_t buf = scratch_u32 + (Cfg::kStageBufs == 2 ? (st.store_seq & 1u) * 2048u : 0u);
-          // the TMA store that last read this buffer must be done with it
-          if (lane == 0) bulk_wait_group_read<Cfg::kStageBufs - 1>();
-          __syncwarp();
+          const uint32_t buf = scratch_u32 + (RT == 1 ? ci * 2048u : (Cfg::kSlabs == 2 ? (st.store_seq & 1u) * 2048u : 0u));
+          if constexpr (RT == 0) {
+            // the TMA store that last read this slab must be done with it
+            if (lane == 0) bulk_wait_group_read<Cfg::kSlabs - 1>();
+            __syncwarp();
+          } else {
+            // without a residual nothing has waited for the previous tile's store of this slab yet
+            if (!use_res) {
+              if (lane == 0) bulk_wait_group_read<kMine - 1>();
+              __syncwarp();
+            }
+          }
           if constexpr (MODE == SG_EPI_GEGLU) {
             const uint32_t row = buf + lane * 32;
             const int sw = (lane >> 2) & 1;
@@ -324,6 +388,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
           }
         }
       }
+    }
+  }
+  if constexpr (RT == 1) {
+    if (use_res) {
+      if (!res_waited) mbar_wait(res_bar, st.res_phase);  // (tile without a valid chunk for this warp: nothing was requested)
+      st.res_phase ^= 1;
     }
   }
   if constexpr (MODE == SG_EPI_LINEAR) {

@@ -138,6 +138,15 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_group_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
+// run-time count (0..3); resolved to immediates when the caller's loop is unrolled
+__device__ __forceinline__ void bulk_wait_group_read_n(int n) {
+  switch (n) {
+    case 0: bulk_wait_group_read<0>(); break;
+    case 1: bulk_wait_group_read<1>(); break;
+    case 2: bulk_wait_group_read<2>(); break;
+    default: bulk_wait_group_read<3>(); break;
+  }
+}
 template <int N>
 __device__ __forceinline__ void bulk_wait_group() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");

@@ -286,10 +286,10 @@ class UNetEngine:
         x = xa.t
         xn = self._gn(xa, None, p["gn"], 1e-6, False)
 
-        def row_stats(ncols):
-            return torch.empty(ops.row_stat_parts((m, 1, 1), ncols), m, 2, dtype=F32, device=self.dev)
+        def row_stats(ncols, ktot):
+            return torch.empty(ops.row_stat_parts((m, 1, 1), ncols, ktot), m, 2, dtype=F32, device=self.dev)
 
-        h0, rs0 = self._new(m, c), row_stats(c)
+        h0, rs0 = self._new(m, c), row_stats(c, c)
         ops.linear(xn.view(m, c), p["w_in"], h0, bias=p["b_in"], row_stats_out=rs0)
         # --- self attention (LN1 folded into the QKV projection)
         qkv = self._new(m, 3 * c)
@@ -297,7 +297,7 @@ class UNetEngine:
         a1 = self._new(m, c)
         st = (hw * 3 * c, 3 * c)
         ops.attention(qkv, qkv[:, c:], qkv[:, 2 * c:], a1, n, heads, hd, hw, hw, st, st, st)
-        h1, rs1 = self._new(m, c), row_stats(c)  # residual stream after self-attention == the tapped diffusion feature
+        h1, rs1 = self._new(m, c), row_stats(c, c)  # residual stream after self-attention == the tapped diffusion feature
         ops.linear(a1, p["w_o1"], h1, bias=p["b_o1"], residual=h0, row_stats_out=rs1)
         # --- text (+ image) cross attention (LN2 / LN4 folded into the Q projections)
         q2 = self._new(m, c)
@@ -307,7 +307,7 @@ class UNetEngine:
         kv2 = text_kv[:, p["kv2_off"]:]
         a2 = self._new(m, c)
         ops.attention(q2, kv2, kv2[:, c:], a2, n, heads, hd, hw, L, (hw * c, c), (L * ld, ld), (L * ld, ld))
-        h2, rs2 = self._new(m, c), row_stats(c)
+        h2, rs2 = self._new(m, c), row_stats(c, 2 * c if image is not None else c)
         if image is not None:
             q3 = self._new(m, c)
             ops.linear(h1, p["q3"][0], q3, bias=p["q3"][2], ln=(rs1, p["q3"][1], 1e-5))

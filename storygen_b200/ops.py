@@ -74,15 +74,16 @@ def tile_box(w: int, h: int, n: int) -> Tuple[int, int, int]:
 _PARTS_CACHE = {}
 
 
-def row_stat_parts(grid: Tuple[int, int, int], n_cols: int) -> int:
-    """Number of row-statistics partials a GEMM with this output grid and N writes per row (sg_gemm_row_stat_parts)."""
-    key = (grid, n_cols, torch.cuda.current_device())
+def row_stat_parts(grid: Tuple[int, int, int], n_cols: int, k_total: int) -> int:
+    """Number of row-statistics partials a LINEAR-mode GEMM with this output grid, N and K writes per row
+    (sg_gemm_row_stat_parts: 2 x its N tiles, whose width depends on N, K and the tile count)."""
+    key = (grid, n_cols, k_total, torch.cuda.current_device())
     v = _PARTS_CACHE.get(key)
     if v is None:
         a = SgGemmArgs()
         a.out_w, a.out_h, a.out_n = grid
         a.bw, a.bh, a.bn = tile_box(*grid)
-        a.N = n_cols
+        a.N, a.Ktot, a.mode = n_cols, k_total, SG_EPI_LINEAR
         v = _lib.load().sg_gemm_row_stat_parts(C.byref(a))
         if v < 0:
             _lib.check(v, "sg_gemm_row_stat_parts")
@@ -163,6 +164,9 @@ def gemm(srcs: Sequence[Src], segs: Sequence[Tuple[int, int, int, int, int]], gr
         a.out_stride_w, a.out_stride_h, a.out_stride_n = out_strides
     if row_stats_out is not None:
         _req(row_stats_out, torch.float32, "row_stats_out")
+        want = _lib.load().sg_gemm_row_stat_parts(C.byref(a))
+        if row_stats_out.shape[0] != want or row_stats_out.shape[1] != grid[0] * grid[1] * grid[2]:
+            raise ValueError(f"row_stats_out must be ({want}, M, 2) for this GEMM, got {tuple(row_stats_out.shape)}")
         a.row_stats_out = row_stats_out.data_ptr()
     if col_stats_out is not None:
         _req(col_stats_out, torch.float32, "col_stats_out")

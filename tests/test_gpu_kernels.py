@@ -260,7 +260,7 @@ def test_layernorm_folded_into_producer_and_consumer_gemms(m, k, n, kprod):
     a, w0 = rnd(m, kprod, seed=1), rnd(k, kprod, scale=kprod ** -0.5, seed=2)
     b0, r = rnd(k, seed=3, dtype=torch.float32), rnd(m, k, seed=4)
     x = torch.empty(m, k, dtype=BF16, device=DEV)
-    rs = torch.empty(ops.row_stat_parts((m, 1, 1), k), m, 2, dtype=torch.float32, device=DEV)
+    rs = torch.empty(ops.row_stat_parts((m, 1, 1), k, kprod), m, 2, dtype=torch.float32, device=DEV)
     ops.linear(a, w0, x, bias=b0, residual=r, res_scale=2.0, row_stats_out=rs)
     xf = x.float()
     tot = rs.sum(0)  # (m, 2): sum, sumsq of every row, taken in fp32 BEFORE the final bf16 rounding of x
@@ -283,7 +283,7 @@ def test_layernorm_folded_into_producer_and_consumer_gemms(m, k, n, kprod):
 def test_layernorm_folded_geglu_consumer():
     m, c = 512, 320
     x = rnd(m, c, seed=1)
-    rs = torch.empty(ops.row_stat_parts((m, 1, 1), c), m, 2, dtype=torch.float32, device=DEV)
+    rs = torch.empty(ops.row_stat_parts((m, 1, 1), c, c), m, 2, dtype=torch.float32, device=DEV)
     eye = torch.eye(c).to(BF16).to(DEV)
     x2 = torch.empty_like(x)
     ops.linear(x, eye, x2, row_stats_out=rs)  # identity producer: x2 == x, emits the row partials
