@@ -15,14 +15,20 @@
 // K loop = list of segments (source tensor, dx, dy, first channel, #64-channel blocks): this one
 // kernel is Linear, 1x1 conv, 3x3 conv (stride 1 or, via phase-strided sources, stride 2), conv over
 // a channel-concat of two tensors, and conv + fused 1x1 shortcut.  See include/storygen_b200.h.
+#include <stdlib.h>
+
 #include "gemm_common.cuh"
 
 namespace sg {
 
-template <int BN, int MODE, int RT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-    gemm_kernel(const __grid_constant__ GemmKParams p) {
-  using Cfg = GemmCfg<BN, RT>;
+// CG = 2: the CTA-pair form.  Two CTAs of a cluster (the two SMs of a TPC) work on two vertically adjacent M tiles and the
+// same N tile: each loads its own A tile and HALF of the B tile, the leader (cluster rank 0) issues tcgen05.mma.cta_group::2
+// with M = 256 and commits to the barriers of both CTAs, each CTA's epilogue drains its own 128 accumulator rows.  Per
+// k-block a CTA stages 16 KB + 64 B x BN instead of 16 KB + 128 B x BN: the operand ingest that bounds the K-heavy
+// convolutions (and a good part of their power) drops by a quarter to a third.
+template <int BN, int MODE, int RT, int CG>
+__device__ __forceinline__ void gemm_kernel_impl(const GemmKParams& p) {
+  using Cfg = GemmCfg<BN, RT, CG>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -41,7 +47,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // broadcast: the compiler treats it as warp-uniform
   const int lane = threadIdx.x & 31;
   const int num_m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  const int num_tiles = num_m_tiles * p.num_n_tiles;
+  // work items: CG = 1: (M tile, N tile); CG = 2: (pair of M tiles, N tile), this CTA taking M tile 2 * pair + rank
+  const int num_tiles = ((num_m_tiles + CG - 1) / CG) * p.num_n_tiles;
+  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_item = blockIdx.x / CG, item_step = gridDim.x / CG;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -50,14 +59,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], kEpiWarps * CG);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) {
+    if constexpr (CG == 2) tmem_alloc2(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers are initialised before anything is sent to them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform for the compiler
 
@@ -66,19 +79,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (lane == 0) tma_prefetch_desc(&p.b_map);
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / p.num_n_tiles;
-      const int nt = tile - mt * p.num_n_tiles;
+    for (int tile = first_item; tile < num_tiles; tile += item_step) {
+      const int mt = (tile / p.num_n_tiles) * CG + cta_rank;  // past the last M tile (odd count): TMA zero-fills
+      const int nt = tile % p.num_n_tiles;
       const int tx = mt % p.tiles_x;
       const int ty = (mt / p.tiles_x) % p.tiles_y;
       const int tn = mt / (p.tiles_x * p.tiles_y);
       const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tn * p.bn;
+      // CG = 2: this CTA's half of the N tile's (possibly ragged) columns
+      const int ncols = (p.N - nt * BN) < BN ? (p.N - nt * BN) : BN;
+      const int b_row0 = nt * BN + cta_rank * (ncols / 2);
       int kb = 0;
       for (int s = 0; s < p.num_segs; ++s) {
         const sg_seg seg = p.segs[s];
         const CUtensorMap* amap = &p.a_maps[seg.src];
         for (int j = 0; j < seg.nkb; ++j, ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if constexpr (CG == 2) {
+            // both CTAs' bytes complete on the LEADER's barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx_w(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const uint32_t lb = leader_bar_addr(&full_bar[stage]);
+            tma_load_4d_2cta_w(smem_a + stage * Cfg::kABytes, amap, lb, seg.c0 + j * kBK, x0 + seg.dx, y0 + seg.dy, n0);
+            tma_load_2d_2cta_w(smem_b + stage * Cfg::kBBytes, &p.b_map, lb, kb * kBK, b_row0);
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx_w(&full_bar[stage], Cfg::kStageBytes);
           tma_load_4d_w(smem_a + stage * Cfg::kABytes, amap, &full_bar[stage], seg.c0 + j * kBK, x0 + seg.dx,
                         y0 + seg.dy, n0);
@@ -91,18 +119,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+    // ===================== MMA issuer (whole warp, one elected lane issues; CG = 2: the leader CTA only) =====================
+    if (CG == 1 || cta_rank == 0) {
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     int mma_tile = 0;
     const uint32_t a_addr0 = smem_u32(smem_a), b_addr0 = smem_u32(smem_b);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = first_item; tile < num_tiles; tile += item_step) {
       // the last N tile may be ragged (e.g. N = 640 as 256 + 256 + 128): issue only the columns that exist
       const int nt_mma = tile % p.num_n_tiles;
       const int ncols = (p.N - nt_mma * BN) < BN ? (p.N - nt_mma * BN) : BN;
-      const uint32_t idesc = make_idesc_bf16(kBM, static_cast<uint32_t>((ncols + 15) & ~15), 0, 0);
+      const uint32_t idesc = make_idesc_bf16(kBM * CG, static_cast<uint32_t>((ncols + 15) & ~15), 0, 0);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && mma_tile < 8) p.dbg[(1 * 8 + mma_tile) * 8 + 0] = clock64();
@@ -115,21 +144,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k) {
           // advance 16 bf16 = 32 bytes inside the swizzle atom: +2 in the (>>4) address field
-          umma_ss_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          if constexpr (CG == 2) umma_ss2_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          else umma_ss_w(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
         }
-        umma_commit_w(&empty_bar[stage]);
+        if constexpr (CG == 2) umma_commit2_w(&empty_bar[stage]);
+        else umma_commit_w(&empty_bar[stage]);
         if (++stage == Cfg::kStages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      umma_commit_w(&tfull_bar[acc]);
+      if constexpr (CG == 2) umma_commit2_w(&tfull_bar[acc]);
+      else umma_commit_w(&tfull_bar[acc]);
       if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && mma_tile < 8) p.dbg[(1 * 8 + mma_tile) * 8 + 1] = clock64();
       ++mma_tile;
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
+    }
     }
   } else {
     // ===================== epilogue (see gemm_common.cuh::epilogue_tile) =====================
@@ -144,16 +177,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       tma_prefetch_desc(&p.out_map);
       if (RT == 1) tma_prefetch_desc(&p.res_map);
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / p.num_n_tiles;
-      const int nt = tile - mt * p.num_n_tiles;
+    for (int tile = first_item; tile < num_tiles; tile += item_step) {
+      const int mt = (tile / p.num_n_tiles) * CG + cta_rank;
+      const int nt = tile % p.num_n_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_tile<BN, MODE, RT>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase, est,
-                                  &res_bar[warp - 2], tile_ord, warp);
+      if (CG == 1 || mt < num_m_tiles) {
+        epilogue_tile<BN, MODE, RT, CG>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase, est,
+                                        &res_bar[warp - 2], tile_ord, warp);
+      } else {
+        mbar_wait(&tfull_bar[acc], acc_phase);  // odd M-tile count: the pair's second half has no rows
+      }
       ++tile_ord;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CG == 2 && cta_rank != 0) mbar_arrive_cluster(&tempty_bar[acc], 0);  // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -164,11 +204,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer may still read this CTA's operands / signal its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc2(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+template <int BN, int MODE, int RT>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmKParams p) {
+  gemm_kernel_impl<BN, MODE, RT, 1>(p);
+}
+template <int BN, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) gemm_pair_kernel(const __grid_constant__ GemmKParams p) {
+  gemm_kernel_impl<BN, MODE, 0, 2>(p);
 }
 
 template <int BN, int MODE, int RT = 0>
@@ -178,6 +229,18 @@ static int launch_gemm_mode(const GemmKParams& kp, int num_tiles, cudaStream_t s
   if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<BN, MODE, RT>), Cfg::kSmemBytes, &configured)) return rc;
   int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   gemm_kernel<BN, MODE, RT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <int BN, int MODE>
+static int launch_gemm_pair(const GemmKParams& kp, int num_pair_tiles, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, 0, 2>;
+  static std::atomic<uint64_t> configured{0};
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_pair_kernel<BN, MODE>), Cfg::kSmemBytes, &configured)) return rc;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (num_pair_tiles < pairs ? num_pair_tiles : pairs);
+  gemm_pair_kernel<BN, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
@@ -341,6 +404,25 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
 
   const int num_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n * kp.num_n_tiles;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  // CTA pairs (cta_group::2) for the K-heavy GEMMs with enough tile pairs to fill the machine: their main loop is bound
+  // by operand ingest / power, and a pair stages each B byte once instead of twice.  SG_GEMM_PAIR=0 disables (A/B runs).
+  static const bool pair_enabled = [] {
+    const char* e = getenv("SG_GEMM_PAIR");
+    return e == nullptr || e[0] != '0';
+  }();
+  const int num_m_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n;
+  const int num_pair_tiles = ((num_m_tiles + 1) / 2) * kp.num_n_tiles;
+  if (pair_enabled && a->mode == SG_EPI_LINEAR && !res_tma && total_kb >= 32 && num_pair_tiles >= num_sms() / 2 &&
+      (bn_tile == 256 || bn_tile == 160)) {
+    // the pair's B box holds half of the N tile's rows
+    uint64_t dims[2] = {static_cast<uint64_t>(a->Ktot), static_cast<uint64_t>(a->N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(a->Ktot) * 2};
+    uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(bn_tile / 2)};
+    int rc = encode_tmap_bf16(&kp.b_map, a->b, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != 0) return rc;
+    return bn_tile == 256 ? launch_gemm_pair<256, SG_EPI_LINEAR>(kp, num_pair_tiles, stream)
+                          : launch_gemm_pair<160, SG_EPI_LINEAR>(kp, num_pair_tiles, stream);
+  }
   switch (bn_tile) {
     case 256: return launch_gemm<256>(kp, num_tiles, false, stream);
     case 160: return launch_gemm<160>(kp, num_tiles, res_tma, stream);

@@ -54,10 +54,11 @@ struct GemmKParams {
 //           every thread adds its row in place and the same slab is the TMA store's source.  For the small-K GEMMs of
 //           the transformer blocks (K = C or 2C), whose epilogue is the critical path: a row-per-thread global read costs
 //           one L1 wavefront per 16 bytes, the bulk copy none.
-template <int BN, int RT = 0>
+//   CG = 2: CTA pair (cta_group::2): this CTA stages only its half of the B tile.
+template <int BN, int RT = 0, int CG = 1>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kMine = (BN / 32 + 1) / 2;  // chunks of a tile per epilogue warp
   static constexpr int kSlabs = RT ? kMine : ((BN == 256) ? 1 : 2);
@@ -90,6 +91,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-0.70710678f * z, e, fmaxf(x, 0.f));  // 0.5 |x| = z / sqrt(2)
 }
 
+// two gelu_erf at once with packed fp32 arithmetic (same polynomial): 17 instead of 34 issue slots per pair
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const float2 z = make_float2(fminf(fabsf(x.x) * 0.70710678f, 6.0f), fminf(fabsf(x.y) * 0.70710678f, 6.0f));
+  float2 q = ffma2(z, make_float2(-1.2884705e-05f, -1.2884705e-05f), make_float2(3.6014518e-04f, 3.6014518e-04f));
+  q = ffma2(q, z, make_float2(-4.3878024e-03f, -4.3878024e-03f));
+  q = ffma2(q, z, make_float2(3.1177560e-02f, 3.1177560e-02f));
+  q = ffma2(q, z, make_float2(-1.4790413e-01f, -1.4790413e-01f));
+  q = ffma2(q, z, make_float2(-9.2054057e-01f, -9.2054057e-01f));
+  q = ffma2(q, z, make_float2(-1.6271738f, -1.6271738f));
+  const float2 t = fmul2(q, z);
+  const float2 e = make_float2(fast_exp2(t.x), fast_exp2(t.y));  // erfc(|x| / sqrt(2))
+  return ffma2(fmul2(z, make_float2(-0.70710678f, -0.70710678f)), e, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
+
 // State an epilogue warp carries from tile to tile: which staging buffer comes next (the TMA stores of earlier tiles may
 // still be reading the other one).
 struct EpiState {
@@ -110,12 +125,12 @@ struct EpiState {
 // are column sums of that same slab.  Before the accumulator is awaited the warp has already fetched its residual row
 // segments, the bias / csum vectors of all its chunks and its row's LayerNorm statistics, so their latency overlaps
 // the tile's main loop; TMEM loads are double-buffered.
-template <int BN, int MODE, int RT>
+template <int BN, int MODE, int RT, int CG = 1>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt, const int nt, const uint32_t t_row,
                                               uint8_t* scratch, const int quarter, const int grp, const int lane,
                                               uint64_t* tfull, const uint32_t tfull_phase, EpiState& st, uint64_t* res_bar,
                                               const int tile_ord = 0, const int warp_id = 0) {
-  using Cfg = GemmCfg<BN, RT>;
+  using Cfg = GemmCfg<BN, RT, CG>;
   static_assert(RT == 0 || MODE == SG_EPI_LINEAR, "TMA residual slabs: LINEAR epilogue only");
   const bool dbg_on = (p.dbg != nullptr) && blockIdx.x == 0 && lane == 0 && tile_ord < 8;
 #define SG_GT(slot) do { if (dbg_on) p.dbg[(warp_id * 8 + tile_ord) * 8 + (slot)] = clock64(); } while (0)
@@ -148,7 +163,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
   const int slab_n = tn * p.bn + (r0 >> (p.bw_log2 + p.bh_log2));
 
   // ---- before the accumulator is awaited: everything that comes from global memory -------------------------------
-  uint4 res[(MODE == SG_EPI_LINEAR && RT == 0) ? kMine : 1][4];
+  // RT = 0: the row's residual segment of the NEXT chunk is fetched while the current one is processed (the first
+  // before the accumulator is awaited); two register sets instead of one per chunk
+  [[maybe_unused]] uint4 res[2][4];
+  [[maybe_unused]] auto fetch_res = [&](const int ci, uint4 (&dst)[4]) {
+    const int col0 = nt * BN + (grp + 2 * ci) * 32;
+    if (use_res && row_ok && grp + 2 * ci < kChunks && col0 < p.N) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col0) + i);
+    }
+  };
   if constexpr (RT == 1) {
     __syncwarp();  // every lane is done with the previous tile's slabs (column statistics read them)
     // residual slabs by TMA into the slabs the output will leave from; slab ci is free once the store that read it in the
@@ -169,18 +193,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
       }
     }
   }
-  if constexpr (MODE == SG_EPI_LINEAR && RT == 0) {
-    if (use_res && row_ok) {
-#pragma unroll
-      for (int ci = 0; ci < kMine; ++ci) {
-        const int col0 = nt * BN + (grp + 2 * ci) * 32;
-        if (grp + 2 * ci < kChunks && col0 < p.N) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) res[ci][i] = __ldg(reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col0) + i);
-        }
-      }
-    }
-  }
+  if constexpr (MODE == SG_EPI_LINEAR && RT == 0) fetch_res(0, res[0]);
   // previous tile's readers of the vectors are done (they finished the tile before arriving on tempty / looping here)
   __syncwarp();
 #pragma unroll
@@ -203,7 +216,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
     ln_rstd = rsqrtf(fmaxf(q * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
   }
   __syncwarp();
-  float rs_acc = 0.f, rq_acc = 0.f;  // per-row (sum, sumsq) of this warp's columns of the output
+  float2 rs2_acc = make_float2(0.f, 0.f), rq2_acc = make_float2(0.f, 0.f);  // per-row (sum, sumsq) of this warp's columns
   bool res_waited = false;
 
   SG_GT(1);
@@ -217,43 +230,52 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
     const int c = grp + 2 * ci;
     if (c < kChunks) {  // warp-uniform
       tmem_ld_wait();
-      if (ci + 1 < kMine && c + 2 < kChunks) tmem_ld32(t_row + (c + 2) * 32, v[(ci + 1) & 1]);  // overlaps the math below
+      if (ci + 1 < kMine && c + 2 < kChunks) {  // overlap the math below
+        tmem_ld32(t_row + (c + 2) * 32, v[(ci + 1) & 1]);
+        if constexpr (MODE == SG_EPI_LINEAR && RT == 0) fetch_res(ci + 1, res[(ci + 1) & 1]);
+      }
       const int col0 = nt * BN + c * 32;
       if (col0 < p.N) {  // warp-uniform
-        float f[32];
+        // the chunk as 16 column pairs: every step below is packed fp32 (f32x2) or bf16x2 arithmetic, one issue slot per
+        // two elements (the small-K GEMMs are bound by the epilogue's instruction count)
+        float2 f[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[ci & 1][j]);
+        for (int j = 0; j < 16; ++j) f[j] = make_float2(__uint_as_float(v[ci & 1][2 * j]), __uint_as_float(v[ci & 1][2 * j + 1]));
         if (use_ln) {
-          // LN(x) W^T = rstd (x W'^T - mean csum): acc holds x W'^T
-          const float nm = -ln_mean;
+          // LN(x) W^T + b' = rstd (x W'^T - mean csum) + b': acc holds x W'^T
+          const float2 nm = make_float2(-ln_mean, -ln_mean), rs2 = make_float2(ln_rstd, ln_rstd);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint4 cc = lds128(csum_u32 + ci * 128 + j * 16);  // same address in every lane: broadcast
-            f[4 * j + 0] = ln_rstd * fmaf(nm, __uint_as_float(cc.x), f[4 * j + 0]);
-            f[4 * j + 1] = ln_rstd * fmaf(nm, __uint_as_float(cc.y), f[4 * j + 1]);
-            f[4 * j + 2] = ln_rstd * fmaf(nm, __uint_as_float(cc.z), f[4 * j + 2]);
-            f[4 * j + 3] = ln_rstd * fmaf(nm, __uint_as_float(cc.w), f[4 * j + 3]);
+            f[2 * j] = ffma2(make_float2(__uint_as_float(cc.x), __uint_as_float(cc.y)), nm, f[2 * j]);
+            f[2 * j + 1] = ffma2(make_float2(__uint_as_float(cc.z), __uint_as_float(cc.w)), nm, f[2 * j + 1]);
           }
-        }
-        if (p.bias != nullptr) {
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 bb = lds128(bias_u32 + ci * 128 + j * 16);
+              f[2 * j] = ffma2(f[2 * j], rs2, make_float2(__uint_as_float(bb.x), __uint_as_float(bb.y)));
+              f[2 * j + 1] = ffma2(f[2 * j + 1], rs2, make_float2(__uint_as_float(bb.z), __uint_as_float(bb.w)));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmul2(f[j], rs2);
+          }
+        } else if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint4 bb = lds128(bias_u32 + ci * 128 + j * 16);
-            f[4 * j + 0] += __uint_as_float(bb.x);
-            f[4 * j + 1] += __uint_as_float(bb.y);
-            f[4 * j + 2] += __uint_as_float(bb.z);
-            f[4 * j + 3] += __uint_as_float(bb.w);
+            f[2 * j] = fadd2(f[2 * j], make_float2(__uint_as_float(bb.x), __uint_as_float(bb.y)));
+            f[2 * j + 1] = fadd2(f[2 * j + 1], make_float2(__uint_as_float(bb.z), __uint_as_float(bb.w)));
           }
         }
         if (lane_bias_row != nullptr && row_ok) {
           const float4* b4 = reinterpret_cast<const float4*>(lane_bias_row + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float4 bb = __ldg(b4 + j);
-            f[4 * j + 0] += bb.x;
-            f[4 * j + 1] += bb.y;
-            f[4 * j + 2] += bb.z;
-            f[4 * j + 3] += bb.w;
+            const float4 bb = __ldg(b4 + j);
+            f[2 * j] = fadd2(f[2 * j], make_float2(bb.x, bb.y));
+            f[2 * j + 1] = fadd2(f[2 * j + 1], make_float2(bb.z, bb.w));
           }
         }
         if constexpr (MODE == SG_EPI_NCHW_F32) {
@@ -264,8 +286,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
             const long long base =
                 static_cast<long long>(n) * p.out_channels * plane + static_cast<long long>(y) * p.out_w + x;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < p.out_channels) of[base + j * plane] = f[j];
+            for (int j = 0; j < 16; ++j) {
+              if (2 * j < p.out_channels) of[base + (2 * j) * plane] = f[j].x;
+              if (2 * j + 1 < p.out_channels) of[base + (2 * j + 1) * plane] = f[j].y;
+            }
           }
         } else {
           // ---- bf16 chunk of this row: 16 (LINEAR) / 8 (GEGLU) packed words
@@ -274,16 +298,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
           if constexpr (MODE == SG_EPI_GEGLU) {
             // columns [0,16) = value, [16,32) = gate (weights pre-interleaved on the host)
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              w[j] = pack_bf16x2(f[2 * j] * gelu_erf(f[16 + 2 * j]), f[2 * j + 1] * gelu_erf(f[17 + 2 * j]));
+            for (int j = 0; j < 8; ++j) {
+              const float2 o = fmul2(f[j], gelu_erf2(f[8 + j]));
+              w[j] = pack_bf16x2(o.x, o.y);
+            }
           } else {
-            // (acc + bias) is rounded to bf16 before the residual add, exactly like the reference's separate Linear / add
-            // ops under autocast; the row statistics are taken from the fp32 value just before the final rounding
+            // (acc + bias) is rounded to bf16, then the residual is added with ONE rounding (bf16x2 fma), like the reference's
+            // separate Linear and add ops under autocast
 #pragma unroll
-            for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-            [[maybe_unused]] uint32_t rw[16];
-            if constexpr (RT == 1) {
-              if (use_res) {
+            for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(f[j].x, f[j].y);
+            if (use_res) {
+              const uint32_t sc = pack_bf16x2(p.res_scale, p.res_scale);
+              if constexpr (RT == 1) {
                 // this row of the residual slab (TMA wrote it with the store's swizzle)
                 if (!res_waited) {
                   mbar_wait(res_bar, st.res_phase);
@@ -294,32 +320,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const uint4 q = lds128(rrow + ((j ^ sw) << 4));
-                  rw[4 * j] = q.x; rw[4 * j + 1] = q.y; rw[4 * j + 2] = q.z; rw[4 * j + 3] = q.w;
+                  w[4 * j] = hfma2_bf16(sc, q.x, w[4 * j]);
+                  w[4 * j + 1] = hfma2_bf16(sc, q.y, w[4 * j + 1]);
+                  w[4 * j + 2] = hfma2_bf16(sc, q.z, w[4 * j + 2]);
+                  w[4 * j + 3] = hfma2_bf16(sc, q.w, w[4 * j + 3]);
                 }
-              }
-            } else {
-              if (use_res) {
+              } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const uint4 q = res[ci][j];
-                  rw[4 * j] = q.x; rw[4 * j + 1] = q.y; rw[4 * j + 2] = q.z; rw[4 * j + 3] = q.w;
+                  const uint4 q = res[ci & 1][j];
+                  w[4 * j] = hfma2_bf16(sc, q.x, w[4 * j]);
+                  w[4 * j + 1] = hfma2_bf16(sc, q.y, w[4 * j + 1]);
+                  w[4 * j + 2] = hfma2_bf16(sc, q.z, w[4 * j + 2]);
+                  w[4 * j + 3] = hfma2_bf16(sc, q.w, w[4 * j + 3]);
                 }
               }
             }
-            if (use_res || row_out) {
+            if (row_out) {
+              // per-row (sum, sumsq) of the values as stored
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                float2 a = unpack_bf16x2(w[j]);
-                if (use_res) {
-                  const float2 rr = unpack_bf16x2(rw[j]);
-                  a.x = fmaf(p.res_scale, rr.x, a.x);
-                  a.y = fmaf(p.res_scale, rr.y, a.y);
-                  w[j] = pack_bf16x2(a.x, a.y);
-                }
-                if (row_out) {
-                  rs_acc += a.x + a.y;
-                  rq_acc = fmaf(a.x, a.x, fmaf(a.y, a.y, rq_acc));
-                }
+                const float2 a = bf16x2_to_float2(w[j]);
+                rs2_acc = fadd2(rs2_acc, a);
+                rq2_acc = ffma2(a, a, rq2_acc);
               }
             }
             if (!row_ok) {  // rows outside the image: TMA clips them; zeros keep them out of the column statistics
@@ -328,10 +351,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
             }
           }
           // ---- staging slab: [32 rows x 64 B] swizzle-64B (LINEAR) / [32 rows x 32 B] swizzle-32B (GEGLU)
-          const uint32_t buf = scratch_u32 + (RT == 1 ? ci * 2048u : (Cfg::kSlabs == 2 ? (st.store_seq & 1u) * 2048u : 0u));
+          // GEGLU slabs are 1 KB: two of them alternate inside one 2 KB region even when the configuration has a single one
+          constexpr int kAlt = (MODE == SG_EPI_GEGLU) ? 2 * Cfg::kSlabs : Cfg::kSlabs;
+          constexpr uint32_t kSlabPitch = (MODE == SG_EPI_GEGLU) ? 1024u : 2048u;
+          const uint32_t buf = scratch_u32 + (RT == 1 ? ci * 2048u : (st.store_seq % kAlt) * kSlabPitch);
           if constexpr (RT == 0) {
             // the TMA store that last read this slab must be done with it
-            if (lane == 0) bulk_wait_group_read<Cfg::kSlabs - 1>();
+            if (lane == 0) bulk_wait_group_read<kAlt - 1>();
             __syncwarp();
           } else {
             // without a residual nothing has waited for the previous tile's store of this slab yet
@@ -366,20 +392,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
               // consumer's GroupNorm will see): lane = (row parity, column pair); rows 2k / 2k+1 are 64 B apart, so the
               // two half-warps hit disjoint banks
               const int cp = lane & 15, hf = lane >> 4;
-              float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+              float2 cs = make_float2(0.f, 0.f), cq = make_float2(0.f, 0.f);
 #pragma unroll
               for (int k = 0; k < 16; ++k) {
                 const int rr = 2 * k + hf;
-                const float2 e = unpack_bf16x2(lds32(buf + rr * 64 + ((((cp >> 2) ^ ((rr >> 1) & 3))) << 4) + (cp & 3) * 4));
-                s0 += e.x;
-                q0 = fmaf(e.x, e.x, q0);
-                s1 += e.y;
-                q1 = fmaf(e.y, e.y, q1);
+                const float2 e = bf16x2_to_float2(lds32(buf + rr * 64 + ((((cp >> 2) ^ ((rr >> 1) & 3))) << 4) + (cp & 3) * 4));
+                cs = fadd2(cs, e);
+                cq = ffma2(e, e, cq);
               }
-              s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-              q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
-              s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-              q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+              const float s0 = cs.x + __shfl_xor_sync(0xffffffffu, cs.x, 16);
+              const float q0 = cq.x + __shfl_xor_sync(0xffffffffu, cq.x, 16);
+              const float s1 = cs.y + __shfl_xor_sync(0xffffffffu, cs.y, 16);
+              const float q1 = cq.y + __shfl_xor_sync(0xffffffffu, cq.y, 16);
               if (lane < 16)
                 *reinterpret_cast<float4*>(reinterpret_cast<float2*>(p.col_stats_out) +
                                            (static_cast<long long>(mt) * 4 + quarter) * p.N + col0 + 2 * cp) =
@@ -398,7 +422,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
   }
   if constexpr (MODE == SG_EPI_LINEAR) {
     if (row_out && row_ok)
-      reinterpret_cast<float2*>(p.row_stats_out)[static_cast<long long>(nt * 2 + grp) * p.M + m] = make_float2(rs_acc, rq_acc);
+      reinterpret_cast<float2*>(p.row_stats_out)[static_cast<long long>(nt * 2 + grp) * p.M + m] = make_float2(rs2_acc.x + rs2_acc.y, rq2_acc.x + rq2_acc.y);
   }
   SG_GT(3);
 #undef SG_GT

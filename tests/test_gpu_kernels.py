@@ -366,3 +366,35 @@ def test_upsample_conv_as_four_subpixel_phases(n, h, w, c):
     ops.groupnorm_from_parts(out.view(n, H * W, c), cs, None, None, n, H * W, 32, 1e-5, gamma, beta, False, y, mr)
     refn = F.group_norm(out.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5).permute(0, 2, 3, 1).reshape(n, H * W, c)
     close(y, refn, rel=0.015, abs_=0.03)
+
+
+@pytest.mark.parametrize("m,k,n,res", [(128 * 150, 2048, 512, False), (128 * 151, 2048, 640, True), (128 * 160, 4096, 320, True)])
+def test_linear_cta_pair_path(m, k, n, res):
+    """K-heavy GEMMs with >= 74 tile pairs run as CTA pairs (cta_group::2, gemm.cu gemm_pair_kernel): M = 256 per MMA, each CTA
+    stages half of B.  Odd M-tile count (151), ragged last N tile (640 = 256 + 256 + 128), residual, row statistics."""
+    x, w = rnd(m, k, seed=11), rnd(n, k, scale=k ** -0.5, seed=12)
+    b = rnd(n, seed=13, dtype=torch.float32)
+    r = rnd(m, n, seed=14) if res else None
+    out = torch.empty(m, n, dtype=BF16, device=DEV)
+    rs = torch.empty(ops.row_stat_parts((m, 1, 1), n, k), m, 2, dtype=torch.float32, device=DEV)
+    ops.linear(x, w, out, bias=b, residual=r, row_stats_out=rs)
+    ref = x.float() @ w.float().T + b + (r.float() if res else 0)
+    close(out, ref)
+    assert torch.allclose(rs.sum(0)[:, 0], ref.sum(1), rtol=2e-3, atol=0.05 * n ** 0.5)
+
+
+def test_conv3x3_cta_pair_path_with_groupnorm_statistics():
+    n, h, w, cin, cout = 4, 64, 64, 256, 320
+    x = rnd(n, h, w, cin, seed=21)
+    wt = rnd(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=22)
+    b = rnd(cout, seed=23, dtype=torch.float32)
+    out = torch.empty(n, h, w, cout, dtype=BF16, device=DEV)
+    cs = ops.ColStats((w, h, n), cout, DEV)
+    ops.gemm([Src.nhwc(x)], taps3x3(0, cin), (w, h, n), wt, out, bias=b, col_stats_out=cs.rep(0))
+    wref = wt.float().reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wref, b, padding=1).permute(0, 2, 3, 1)
+    close(out, ref)
+    tot = cs.buf[0].view(n, -1, cout, 2).sum(1)  # bn == 1: the blocks of image i are contiguous
+    of = out.float().view(n, h * w, cout)
+    assert torch.allclose(tot[..., 0], of.sum(1), rtol=2e-3, atol=0.5)
+    assert torch.allclose(tot[..., 1], (of * of).sum(1), rtol=2e-3, atol=0.5)
