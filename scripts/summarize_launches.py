@@ -26,7 +26,7 @@ def main(csv_path, trace_path):
     aq = collections.deque(t for t in trace if t[0] == "attn")
     gs, ats = collections.defaultdict(lambda: [0, 0.0]), collections.defaultdict(lambda: [0, 0.0])
     for n, t in launches:
-        if n.startswith("gemm_kernel") and gq:
+        if n.startswith(("gemm_kernel", "gemm_pair_kernel")) and gq:
             _, m, nn, k, segs, mode = gq.popleft()
             gs[(m, nn, k, mode)][0] += 1
             gs[(m, nn, k, mode)][1] += t

@@ -412,14 +412,17 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   }();
   const int num_m_tiles = kp.tiles_x * kp.tiles_y * kp.tiles_n;
   const int num_pair_tiles = ((num_m_tiles + 1) / 2) * kp.num_n_tiles;
-  if (pair_enabled && a->mode == SG_EPI_LINEAR && !res_tma && total_kb >= 32 && num_pair_tiles >= num_sms() / 2 &&
-      (bn_tile == 256 || bn_tile == 160)) {
+  // ... and for wide outputs at any K (N >= 960: the fused QKV projection, the GEGLU up-projection): every M tile re-reads
+  // the whole weight matrix from L2, so their main loop is bound by B traffic, which a pair halves
+  if (pair_enabled && (a->mode == SG_EPI_LINEAR || a->mode == SG_EPI_GEGLU) && !res_tma && (total_kb >= 32 || a->N >= 960) &&
+      num_pair_tiles >= num_sms() / 2 && (bn_tile == 256 || (bn_tile == 160 && a->mode == SG_EPI_LINEAR))) {
     // the pair's B box holds half of the N tile's rows
     uint64_t dims[2] = {static_cast<uint64_t>(a->Ktot), static_cast<uint64_t>(a->N)};
     uint64_t strides[1] = {static_cast<uint64_t>(a->Ktot) * 2};
     uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(bn_tile / 2)};
     int rc = encode_tmap_bf16(&kp.b_map, a->b, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != 0) return rc;
+    if (a->mode == SG_EPI_GEGLU) return launch_gemm_pair<256, SG_EPI_GEGLU>(kp, num_pair_tiles, stream);
     return bn_tile == 256 ? launch_gemm_pair<256, SG_EPI_LINEAR>(kp, num_pair_tiles, stream)
                           : launch_gemm_pair<160, SG_EPI_LINEAR>(kp, num_pair_tiles, stream);
   }
