@@ -398,3 +398,24 @@ def test_conv3x3_cta_pair_path_with_groupnorm_statistics():
     of = out.float().view(n, h * w, cout)
     assert torch.allclose(tot[..., 0], of.sum(1), rtol=2e-3, atol=0.5)
     assert torch.allclose(tot[..., 1], (of * of).sum(1), rtol=2e-3, atol=0.5)
+
+
+def test_geglu_cta_pair_path_with_folded_layernorm():
+    """The GEGLU up-projection of a transformer block at production size class (wide N, small K) runs as CTA pairs."""
+    m, c = 128 * 160, 320
+    x = rnd(m, c, seed=31)
+    rs = torch.empty(ops.row_stat_parts((m, 1, 1), c, c), m, 2, dtype=torch.float32, device=DEV)
+    x2 = torch.empty_like(x)
+    ops.linear(x, torch.eye(c).to(BF16).to(DEV), x2, row_stats_out=rs)
+    g = torch.Generator("cpu").manual_seed(5)
+    w = (torch.randn(8 * c, c, generator=g) * c ** -0.5).to(DEV)
+    b = (torch.randn(8 * c, generator=g) * 0.1).to(DEV)
+    gamma, beta = (1 + 0.1 * torch.randn(c, generator=g)).to(DEV), (0.05 * torch.randn(c, generator=g)).to(DEV)
+    half = 4 * c
+    il = lambda v: torch.stack([v[:half].reshape(-1, 16, *v.shape[1:]), v[half:].reshape(-1, 16, *v.shape[1:])], 1).reshape(2 * half, *v.shape[1:])
+    wp = (w * gamma[None, :]).to(BF16)
+    out = torch.empty(m, half, dtype=BF16, device=DEV)
+    ops.linear(x, il(wp).contiguous(), out, bias=il(w @ beta + b).contiguous(), mode=_lib.SG_EPI_GEGLU,
+               ln=(rs, il(wp.float().sum(1)).contiguous(), 1e-5))
+    y = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5) @ w.T + b
+    close(out, y[:, :half] * F.gelu(y[:, half:]), rel=0.02, abs_=0.03)
