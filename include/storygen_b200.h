@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 8
+#define SG_ABI_VERSION 9
 
 #define SG_ERR_SHAPE (-1)   /* unsupported / inconsistent shape            */
 #define SG_ERR_ALIGN (-2)   /* pointer or stride not 16-byte aligned        */
@@ -152,9 +152,34 @@ typedef struct sg_attn_args {
   const int32_t* kv_map; /* optional device int32[n_lanes]: K/V lane of each Q lane; NULL = identity */
   float scale;        /* softmax scale (head_dim^-0.5)                                        */
   int64_t* debug_timeline; /* bring-up aid: device int64[12*16*8] phase clocks of CTA 0, or NULL     */
+  float* lse; /* optional fp32 [n_lanes, n_heads, nq]: log2-domain log-sum-exp of every score row,
+                 lse2 = log2(sum_k 2^(scale*log2(e)*s_k)), saved for sg_attention_bwd (training)  */
 } sg_attn_args;
 
 int sg_attention(const sg_attn_args* args, void* stream);
+
+/* ---- attention backward (training of the image cross-attention, train_StorySalon_stage2.py:305-332) ----------
+ * Given q, k, v, the forward output o, its row statistics lse (sg_attention) and the output gradient d_o, computes
+ *   dV = P^T dO,  dK = dS^T Q,  dQ = dS K   with P = softmax(scale Q K^T), dS = scale * P o (dO V^T - rowsum(dO o O)),
+ * recomputing P tile by tile on the tensor cores (FlashAttention-2 backward: one CTA per 128-key tile, looping over
+ * the query tiles; S, dP, dV, dK, dQ accumulators in TMEM).  All tensors bf16 (lane, token, channel) with the strides
+ * of sg_attn_args; dq_accum is an fp32 workspace [n_lanes, nq, n_heads * head_dim] that the CALLER zeroes: query-tile
+ * contributions of different key tiles are added with red.global.add (the only non-deterministic summation order
+ * of the library; dk / dv are written once).  head_dim in {32, 40, 64, 80, 128}; K/V lanes == Q lanes.
+ * delta: fp32 workspace [n_lanes, n_heads, nq]. */
+typedef struct sg_attn_bwd_args {
+  const void* q; const void* k; const void* v; const void* o; const void* d_o;
+  const float* lse;
+  float* delta;
+  float* dq_accum;
+  void* dk; void* dv;
+  int64_t q_stride_n, q_stride_t, k_stride_n, k_stride_t, v_stride_n, v_stride_t;
+  int64_t o_stride_n, o_stride_t;    /* of o and d_o                    */
+  int64_t dk_stride_n, dk_stride_t;  /* of dk and dv                    */
+  int32_t n_lanes, n_heads, head_dim, nq, nk;
+  float scale;
+} sg_attn_bwd_args;
+int sg_attention_bwd(const sg_attn_bwd_args* args, void* stream);
 
 /* ---- normalisation / elementwise kernels (HBM-bound) ---------------------------------------- */
 

@@ -11,6 +11,6 @@ q = torch.randn(lanes, nq, c, device="cuda").to(BF16)
 k = torch.randn(lanes, nk, c, device="cuda").to(BF16)
 v = torch.randn(lanes, nk, c, device="cuda").to(BF16)
 o = torch.empty(lanes, nq, c, device="cuda", dtype=BF16)
-for _ in range(3):
+for _ in range(4):
     ops.attention(q, k, v, o, lanes, heads, d, nq, nk, (nq * c, c), (nk * c, c), (nk * c, c))
 torch.cuda.synchronize()

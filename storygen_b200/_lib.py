@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # STORYGEN_B200_LIB: developer override for A/B runs of an alternative in-tree build of the same library
 LIB_PATH = os.environ.get("STORYGEN_B200_LIB") or os.path.join(_HERE, "libstorygen_b200.so")
 
-SG_ABI_VERSION = 8
+SG_ABI_VERSION = 9
 SG_MAX_SRC = 4
 SG_MAX_SEGS = 24
 SG_EPI_LINEAR = 0
@@ -24,6 +24,7 @@ EXPORTS = [
     "sg_gemm", "sg_attention", "sg_groupnorm_ws_floats", "sg_groupnorm_stats", "sg_groupnorm_apply",
     "sg_layernorm", "sg_timestep_features", "sg_small_linear", "sg_upsample2x", "sg_im2col3x3_nchw",
     "sg_add_noise", "sg_cfg_ddim_step", "sg_gemm_row_stat_parts", "sg_groupnorm_finalize", "sg_groupnorm_apply_ms",
+    "sg_attention_bwd",
 ]
 
 
@@ -60,7 +61,16 @@ class SgAttnArgs(C.Structure):
                 ("o_stride_n", C.c_int64), ("o_stride_t", C.c_int64), ("n_lanes", C.c_int32),
                 ("n_heads", C.c_int32), ("head_dim", C.c_int32), ("nq", C.c_int32), ("nk", C.c_int32),
                 ("n_kv_lanes", C.c_int32), ("kv_map", C.c_void_p), ("scale", C.c_float),
-                ("debug_timeline", C.c_void_p)]
+                ("debug_timeline", C.c_void_p), ("lse", C.c_void_p)]
+
+
+class SgAttnBwdArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p), ("d_o", C.c_void_p),
+                ("lse", C.c_void_p), ("delta", C.c_void_p), ("dq_accum", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+                ("q_stride_n", C.c_int64), ("q_stride_t", C.c_int64), ("k_stride_n", C.c_int64), ("k_stride_t", C.c_int64),
+                ("v_stride_n", C.c_int64), ("v_stride_t", C.c_int64), ("o_stride_n", C.c_int64), ("o_stride_t", C.c_int64),
+                ("dk_stride_n", C.c_int64), ("dk_stride_t", C.c_int64), ("n_lanes", C.c_int32), ("n_heads", C.c_int32),
+                ("head_dim", C.c_int32), ("nq", C.c_int32), ("nk", C.c_int32), ("scale", C.c_float)]
 
 
 class LibraryError(RuntimeError):
@@ -94,6 +104,7 @@ def load():
     lib.sg_gemm.argtypes = [C.POINTER(SgGemmArgs), vp]
     lib.sg_gemm_row_stat_parts.argtypes = [C.POINTER(SgGemmArgs)]
     lib.sg_attention.argtypes = [C.POINTER(SgAttnArgs), vp]
+    lib.sg_attention_bwd.argtypes = [C.POINTER(SgAttnBwdArgs), vp]
     lib.sg_groupnorm_ws_floats.argtypes = [i32, i32]
     lib.sg_groupnorm_stats.argtypes = [vp, i32, vp, i32, i32, i32, i32, f32, vp, vp]
     lib.sg_groupnorm_apply.argtypes = [vp, i32, vp, i32, i32, i32, i32, f32, vp, vp, vp, i32, vp, vp]

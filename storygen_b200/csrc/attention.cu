@@ -64,6 +64,7 @@ struct AttnKParams {
   bf16* o;
   long long o_stride_n, o_stride_t;
   const int* kv_map;
+  float* lse;  // optional [lanes][heads][nq]
   long long* dbg;  // optional phase timestamps of CTA (0,0,0): [warp][tile][8] (bring-up aid, NULL in production)
   int nq, nk, n_heads;
   float scale_log2;  // scale * log2(e)
@@ -700,6 +701,8 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
     }
     const float inv_l = 1.0f / l_run;
     const int q = q0 + 128 * tq + r;
+    if (p.lse != nullptr && q < p.nq)  // log2-domain log-sum-exp of the row (for the backward pass)
+      p.lse[(static_cast<long long>(img) * p.n_heads + head) * p.nq + q] = m_used + log2f(l_run);
     bf16* orow = p.o + static_cast<long long>(img) * p.o_stride_n + static_cast<long long>(q) * p.o_stride_t +
                  head * D;
 #pragma unroll
@@ -792,6 +795,7 @@ extern "C" int sg_attention(const sg_attn_args* a, void* stream_v) {
   kp.o_stride_n = a->o_stride_n;
   kp.o_stride_t = a->o_stride_t;
   kp.kv_map = a->kv_map;
+  kp.lse = a->lse;
   kp.dbg = reinterpret_cast<long long*>(a->debug_timeline);
   kp.nq = a->nq;
   kp.nk = a->nk;
