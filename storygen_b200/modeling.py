@@ -194,7 +194,8 @@ class UNet2DConditionOutput:
 class UNet2DConditionModel(nn.Module):
     """Drop-in for the reference's `model.unet_2d_condition.UNet2DConditionModel` (same constructor
     :84-117, same forward signature :338-347, same 798 state-dict keys), executed by hand-written
-    sm_100a kernels (engine.UNetEngine).  Inference only in this round: outputs carry no autograd graph.
+    sm_100a kernels (engine.UNetEngine).  In train() mode with a trainable parameter on the path the forward is
+    autograd-connected (storygen_b200/train.py: attn3 core forward / backward on the kernels, frozen layers as torch ops).
     """
 
     config_name = "config.json"
@@ -340,7 +341,20 @@ class UNet2DConditionModel(nn.Module):
             self._engine = UNetEngine(self)
         return self._engine
 
-    @torch.no_grad()
+    def train(self, mode: bool = True):
+        if mode != self.training:
+            self._engine = None  # weights may have been updated by an optimiser: re-pack before the next inference call
+        return super().train(mode)
+
+    def _needs_autograd(self, image_hidden_states) -> bool:
+        """train() mode with gradients enabled and a trainable parameter on the path: stage 2 trains attn3 only
+        (train_StorySalon_stage2.py:172-177), which the feature passes (no image_hidden_states) never touch."""
+        if not (self.training and torch.is_grad_enabled()):
+            return False
+        if image_hidden_states is not None:
+            return any(p.requires_grad for p in self.parameters())
+        return any(p.requires_grad for n, p in self.named_parameters() if ".attn3." not in n)
+
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
                 encoder_hidden_states: torch.Tensor, image_hidden_states: Optional[Dict[str, torch.Tensor]] = None,
                 class_labels: Optional[torch.Tensor] = None, cross_attention_kwargs: Optional[Dict[str, Any]] = None,
@@ -351,7 +365,17 @@ class UNet2DConditionModel(nn.Module):
         returns an empty dict)."""
         if class_labels is not None:
             raise NotImplementedError("class conditioning is not part of the StoryGen configuration")
-        out, taps = self.engine().forward(sample, timestep, encoder_hidden_states, image_hidden_states)
+        if self.device.type != "cuda":
+            raise RuntimeError("storygen_b200.UNet2DConditionModel runs only on a CUDA (sm_100a) device: move the "
+                               "model with .to('cuda') first (there is no CPU fallback)")
+        if self._needs_autograd(image_hidden_states):
+            from .train import unet_forward_train
+            out, taps = unet_forward_train(self, sample, timestep, encoder_hidden_states, image_hidden_states)
+            if not return_dict:
+                return (out, taps)
+            return UNet2DConditionOutput(sample=out, img_dif_conditions=taps)
+        with torch.no_grad():
+            out, taps = self.engine().forward(sample, timestep, encoder_hidden_states, image_hidden_states)
         if self.dtype in (torch.float16, torch.bfloat16):
             out = out.to(self.dtype)  # the reference returns the sample in the weights' dtype (inference.py:72-74)
         if not return_dict:

@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import SG_EPI_GEGLU, SG_EPI_LINEAR, SG_EPI_NCHW_F32, SgAttnArgs, SgGemmArgs, SgGnParts
+from ._lib import SG_EPI_GEGLU, SG_EPI_LINEAR, SG_EPI_NCHW_F32, SgAttnArgs, SgAttnBwdArgs, SgGemmArgs, SgGnParts
 
 BF16 = torch.bfloat16
 TRACE = None  # set to a list to record (kernel, shape...) of every launch, in order (profiling aid)
@@ -198,9 +198,11 @@ def taps3x3(src: int, cin: int, c0: int = 0) -> List[Tuple[int, int, int, int, i
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, n_lanes: int, n_heads: int,
               head_dim: int, nq: int, nk: int, q_strides: Tuple[int, int], k_strides: Tuple[int, int],
-              v_strides: Tuple[int, int], n_kv_lanes: int = 0, kv_map: Optional[torch.Tensor] = None) -> torch.Tensor:
+              v_strides: Tuple[int, int], n_kv_lanes: int = 0, kv_map: Optional[torch.Tensor] = None,
+              lse: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(Q K^T / sqrt(d)) V per (lane, head); q/k/v may be strided views into fused projections.
-    *_strides = (lane stride, token stride) in elements."""
+    *_strides = (lane stride, token stride) in elements.  lse: optional fp32 (lanes, heads, nq) receiving the log2-domain
+    log-sum-exp of every score row (saved for attention_bwd)."""
     a = SgAttnArgs()
     a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
     a.q_stride_n, a.q_stride_t = q_strides
@@ -212,10 +214,46 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     a.n_kv_lanes = n_kv_lanes
     a.kv_map = _ptr(kv_map)
     a.scale = head_dim ** -0.5
+    if lse is not None:
+        _req(lse, torch.float32, "lse")
+        a.lse = lse.data_ptr()
     if TRACE is not None:
         TRACE.append(("attn", n_lanes, n_heads, head_dim, nq, nk))
     _lib.check(_lib.load().sg_attention(C.byref(a), _stream()), "sg_attention")
     return out
+
+
+ATTN_BWD_HEAD_DIMS = (32, 40, 64, 80, 128)
+
+
+def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, d_o: torch.Tensor, lse: torch.Tensor,
+                  n_heads: int):
+    """Gradients of attention(q, k, v) for contiguous bf16 (lanes, tokens, heads * head_dim) tensors, given the forward
+    output o, its log-sum-exp rows lse and the output gradient d_o.  Returns (dq, dk, dv) in bf16.
+    One sg_attention_bwd call: a row-dot kernel (delta) + the tcgen05 backward kernel."""
+    for t, name in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (d_o, "d_o")):
+        _req(t, BF16, name)
+    _req(lse, torch.float32, "lse")
+    n, nq, c = q.shape
+    nk = k.shape[1]
+    hd = c // n_heads
+    if hd not in ATTN_BWD_HEAD_DIMS:
+        raise NotImplementedError(f"attention_bwd: head dim {hd} (supported: {ATTN_BWD_HEAD_DIMS})")
+    dq_acc = torch.zeros(n, nq, c, dtype=torch.float32, device=q.device)
+    dk, dv = torch.empty_like(k), torch.empty_like(v)
+    delta = torch.empty(n, n_heads, nq, dtype=torch.float32, device=q.device)
+    a = SgAttnBwdArgs()
+    a.q, a.k, a.v, a.o, a.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), d_o.data_ptr()
+    a.lse, a.delta, a.dq_accum, a.dk, a.dv = lse.data_ptr(), delta.data_ptr(), dq_acc.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.q_stride_n, a.q_stride_t = nq * c, c
+    a.k_stride_n, a.k_stride_t = nk * c, c
+    a.v_stride_n, a.v_stride_t = nk * c, c
+    a.o_stride_n, a.o_stride_t = nq * c, c
+    a.dk_stride_n, a.dk_stride_t = nk * c, c
+    a.n_lanes, a.n_heads, a.head_dim, a.nq, a.nk = n, n_heads, hd, nq, nk
+    a.scale = hd ** -0.5
+    _lib.check(_lib.load().sg_attention_bwd(C.byref(a), _stream()), "sg_attention_bwd")
+    return dq_acc.to(BF16), dk, dv
 
 
 def groupnorm(x0: torch.Tensor, x1: Optional[torch.Tensor], n: int, hw: int, groups: int, eps: float,

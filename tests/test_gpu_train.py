@@ -1,0 +1,122 @@
+"""GPU: the training path of StoryGen's stage 2 (train_StorySalon_stage2.py:168-177, 305-332): only the image
+cross-attention `attn3` is trainable.  The attn3 attention core runs forward AND backward on the tcgen05 kernels
+(sg_attention with log-sum-exp rows, sg_attention_bwd); the frozen layers' dgrad rides torch autograd (storygen_b200/train.py).
+
+Checked here: the backward kernel against torch autograd of the same attention in fp32 (tolerance: bf16 rounding of P, dS
+and of the outputs, stated per test), and the gradients of all 64 attn3 matrices of the tiny UNet against the fp32 oracle's
+autograd (== the reference's model/*.py, tests/test_oracle.py)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.make_golden import cond_from_taps, unet_inputs
+from oracle.unet import TINY_CONFIG, OracleUNet
+from oracle.weights import load_seeded
+from storygen_b200 import UNet2DConditionModel, ops
+from storygen_b200.train import ImageAttentionFunction
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF16 = torch.bfloat16
+
+
+def _ref_attention(q, k, v, heads):
+    n, nq, c = q.shape
+    hd = c // heads
+    sp = lambda t: t.view(n, -1, heads, hd).transpose(1, 2)
+    o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v), scale=hd ** -0.5)
+    return o.transpose(1, 2).reshape(n, nq, c)
+
+
+@pytest.mark.parametrize("hd,heads,n,nq,nk", [(40, 8, 2, 300, 260), (64, 2, 3, 128, 384), (32, 2, 2, 1024, 2048),
+                                              (80, 8, 1, 256, 768), (128, 2, 2, 64, 192), (40, 8, 1, 4096, 4096)])
+def test_attention_backward_kernel_vs_torch_autograd(hd, heads, n, nq, nk):
+    g = torch.Generator("cpu").manual_seed(hd + nq)
+    c = heads * hd
+    q = torch.randn(n, nq, c, generator=g).to(BF16).to(DEV)
+    k = torch.randn(n, nk, c, generator=g).to(BF16).to(DEV)
+    v = torch.randn(n, nk, c, generator=g).to(BF16).to(DEV)
+    d_o = torch.randn(n, nq, c, generator=g).to(BF16).to(DEV)
+    o = torch.empty_like(q)
+    lse = torch.empty(n, heads, nq, dtype=torch.float32, device=DEV)
+    ops.attention(q, k, v, o, n, heads, hd, nq, nk, (nq * c, c), (nk * c, c), (nk * c, c), lse=lse)
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, d_o, lse, heads)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    of = _ref_attention(qf, kf, vf, heads)
+    of.backward(d_o.float())
+    # log-sum-exp rows (log2 domain) of the forward
+    s = torch.einsum("nqhd,nkhd->nhqk", q.float().view(n, nq, heads, hd), k.float().view(n, nk, heads, hd)) * hd ** -0.5
+    assert torch.allclose(lse, torch.logsumexp(s, -1) * 1.4426950408889634, atol=2e-2)
+    assert (o.float() - of).abs().max() <= 0.02 + 0.012 * of.abs().max()
+    for got, ref, name in ((dq, qf.grad, "dq"), (dk, kf.grad, "dk"), (dv, vf.grad, "dv")):
+        err = (got.float() - ref).abs().max().item()
+        tol = 0.02 * ref.abs().max().item() + 0.01
+        assert err <= tol, f"{name}: max err {err:.4g} > {tol:.4g} (ref max {ref.abs().max():.4g})"
+
+
+def test_image_attention_function_is_differentiable_end_to_end():
+    g = torch.Generator("cpu").manual_seed(3)
+    n, nq, nk, heads, hd = 2, 256, 512, 2, 64
+    c = heads * hd
+    mk = lambda *s: torch.randn(*s, generator=g).to(DEV).requires_grad_(True)
+    q, k, v = mk(n, nq, c), mk(n, nk, c), mk(n, nk, c)
+    w = torch.randn(n, nq, c, generator=g).to(DEV)
+    (ImageAttentionFunction.apply(q, k, v, heads) * w).sum().backward()
+    got = [t.grad.clone() for t in (q, k, v)]
+    for t in (q, k, v):
+        t.grad = None
+    (_ref_attention(q, k, v, heads) * w).sum().backward()
+    for a, b in zip(got, (q.grad, k.grad, v.grad)):
+        assert (a - b).abs().max() <= 0.03 * b.abs().max() + 0.01
+
+
+def test_stage2_training_step_gradients_match_the_oracle():
+    """One stage-2 step on the tiny UNet: R = 2 feature passes (inference engine, no grad), the denoise pass in train()
+    mode, masked-MSE loss, backward.  The gradients of the 64 attn3 matrices (the only trainable parameters) are compared
+    with the fp32 oracle's autograd; tolerance 8 % of each gradient's max (bf16 autocast through ~60 layers)."""
+    torch.manual_seed(0)
+    ora = load_seeded(OracleUNet(**TINY_CONFIG), 0)
+    mod = UNet2DConditionModel(**TINY_CONFIG)
+    mod.load_state_dict(ora.state_dict())
+    mod = mod.to(DEV)
+    for m_ in (ora, mod):
+        m_.requires_grad_(False)
+        for name, sub in m_.named_modules():
+            if name.endswith("attn3"):
+                for p in sub.parameters():
+                    p.requires_grad = True
+    trainable = [n for n, p in mod.named_parameters() if p.requires_grad]
+    assert len(trainable) == 16 * 5  # to_q / to_k / to_v / to_out.weight + to_out.bias per block
+    n, R = 2, 2
+    x, t, txt = unet_inputs(n, TINY_CONFIG["cross_attention_dim"], hw=32, seed=7)
+    noise = torch.randn(x.shape, generator=torch.Generator("cpu").manual_seed(8))
+    mask = (torch.rand(x.shape, generator=torch.Generator("cpu").manual_seed(9)) > 0.3).float()
+    # feature passes: no trainable parameter on the path (the reference runs them with grad enabled, nothing is recorded)
+    ora.train()
+    mod.train()
+    with torch.no_grad():
+        o_taps = ora(x, t, txt)[1]
+    m_taps = mod(x.to(DEV), t.to(DEV), txt.to(DEV), return_dict=False)[1]
+    assert not any(v.requires_grad for v in m_taps.values())
+    cond_o = cond_from_taps(o_taps, R)
+    cond_m = {k: v.to(DEV) for k, v in cond_o.items()}  # same conditioning for both (isolates the denoise pass)
+    pred_o = ora(x, t, txt, cond_o)[0]
+    loss_o = F.mse_loss(pred_o * (1 - mask), noise * (1 - mask))
+    loss_o.backward()
+    pred_m = mod(x.to(DEV), t.to(DEV), txt.to(DEV), image_hidden_states=cond_m, return_dict=False)[0]
+    assert pred_m.requires_grad
+    loss_m = F.mse_loss(pred_m.float() * (1 - mask.to(DEV)), noise.to(DEV) * (1 - mask.to(DEV)))
+    loss_m.backward()
+    assert abs(loss_m.item() - loss_o.item()) <= 0.02 * abs(loss_o.item()) + 1e-4
+    go = dict(ora.named_parameters())
+    worst = 0.0
+    for name, p in mod.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        ref = go[name].grad
+        assert p.grad is not None and ref is not None, name
+        rel = (p.grad.float().cpu() - ref).abs().max().item() / (ref.abs().max().item() + 1e-12)
+        worst = max(worst, rel)
+        assert rel <= 0.08, f"{name}: grad deviates by {rel:.3f} of its max"
+    print(f"\n[stage-2 step, tiny UNet] loss {loss_m.item():.5f} (oracle {loss_o.item():.5f}); worst attn3 grad deviation {worst:.3f} of max")
