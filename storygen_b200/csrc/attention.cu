@@ -51,12 +51,6 @@ constexpr bool kPingPong2 = SG_ATTN2_PINGPONG != 0;
 #endif
 // bit (i % 8) set: pair i of a 32-column chunk takes both exps on the FMA pipe (0x11 = 1 in 4, 0x49 = 3 in 8, 0x55 = 1 in 2)
 constexpr unsigned kPolyMask2 = SG_ATTN2_POLY_MASK;
-#ifndef SG_ATTN2_PDEFER
-#define SG_ATTN2_PDEFER 0
-#endif
-// 1: chunk 0 of P_j stays in registers until the exps of chunk 1 are done, so the wait for P V_{j-1} (which guards the
-// single P buffer and the O rescale) moves half a chunk later and stops stalling the exp stream
-constexpr bool kPDefer2 = SG_ATTN2_PDEFER != 0;
 constexpr int kPolyEvery = SG_ATTN_POLY_EVERY;  // 0 = all exps on MUFU; 4 = 1 in 4 on the FMA pipe; 2 = 1 in 2  // the other warpgroup may start its exps once chunk kHandoff (of 4) is issued
 
 struct AttnKParams {
@@ -133,7 +127,8 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
   uint64_t* o_done = p_full + 2;         // [2] MMA -> softmax (PV retired)
   uint64_t* s_free = o_done + 2;         // [2] softmax -> MMA (S row-blocks are in registers; kSepP only)
   uint64_t* v_ready = s_free + 2;        // [kSlots] V fixer -> PV issuer (kSumTC)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_ready + kSlots);
+  uint64_t* p_free = v_ready + kSlots;   // [2][4] PV issuer -> softmax: the k-steps that read chunk c of P_t have retired (kSepP)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 8);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // broadcast: provably warp-uniform role index
   const int lane = threadIdx.x & 31;
@@ -157,6 +152,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
       mbar_init(&o_done[i], 1);
       mbar_init(&s_free[i], 4);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&p_free[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -336,7 +332,15 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
               mbar_wait(&p_full[t], j & 1);
               tc_fence_after();
               if (dbg_on && lane == 0 && j < 16) p.dbg[(1 * 16 + j) * 8 + t * 2 + 1] = clock64();
-              pv(Cfg::kColP + t * 64, tile_addr(iv), Cfg::kColO + t * 64, j == 0);
+              // P V_j in four pairs of k-steps; after each pair the 32 keys (16 TMEM columns) of P_t it read are free for
+              // the softmax warps to overwrite with P_t(j+1): they never wait for the whole P V to retire
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                umma_ts_w(tmem_base + Cfg::kColO + t * 64, tmem_base + Cfg::kColP + t * 64 + ks * 8,
+                          make_smem_desc(tile_addr(iv) + ks * 2048, kAtomBytes, 1024, kLayoutSW128), idesc_pv_of(0),
+                          !(j == 0 && ks == 0));
+                if (ks & 1) umma_commit_w(&p_free[t * 4 + (ks >> 1)]);
+              }
               umma_commit_w(&o_done[t]);
             }
             umma_commit_w(&kv_empty[slot_of(iv)]);  // both tiles have used V_j
@@ -458,7 +462,6 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
         max_reset();
         if (kPingPong2) named_bar_sync(1 + tq, 256);
         SG_TS(4);
-        [[maybe_unused]] uint32_t pk0[16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
@@ -483,12 +486,11 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
             if constexpr (!Cfg::kSumTC) sum2[(i >> 1) & 3] = fadd2(sum2[(i >> 1) & 3], e);
             pk[i >> 1] = pack_bf16x2(e.x, e.y);
           }
-          if (c == (kPDefer2 ? 1 : 0) && j > 0) {
-            // P V_{j-1} must have retired before P_j overwrites P_{j-1} and before the O row may be rescaled; its
-            // ~500 clk hide behind the first chunk(s) of exps.  o_done phases are consumed strictly in order.
-            mbar_wait(od, (j - 1) & 1);
-            tc_fence_after();
-            if (__any_sync(0xffffffffu, need)) {
+          if (j > 0) {
+            if (c == 0 && __any_sync(0xffffffffu, need)) {
+              // rare: the row max grew by more than 2^8 -> rescale the O row (and with it the row sum) once P V_{j-1} has retired
+              mbar_wait(od, (j - 1) & 1);
+              tc_fence_after();
 #pragma unroll
               for (int oc = 0; oc < 2; ++oc) {
                 uint32_t ov[32];
@@ -499,18 +501,11 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
                 tmem_st32(o_tmem + oc * 32, ov);
               }
             }
+            // the two k-steps of P V_{j-1} that read this chunk's columns of P have retired (issued ~a tile ago: no stall)
+            mbar_wait(&p_free[tq * 4 + c], (j - 1) & 1);
+            tc_fence_after();
           }
-          if constexpr (kPDefer2) {
-            if (c == 0) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) pk0[i] = pk[i];
-            } else {
-              if (c == 1) tmem_st16(p_tmem, pk0);
-              tmem_st16(p_tmem + c * 16, pk);
-            }
-          } else {
-            tmem_st16(p_tmem + c * 16, pk);
-          }
+          tmem_st16(p_tmem + c * 16, pk);
           if (kPingPong2 && c == kHandoff && !(tq == 1 && j == T - 1)) named_bar_arrive(2 - tq, 256);
           if constexpr (kHasNext) {
             if (c == 0) {
