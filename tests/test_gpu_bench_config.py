@@ -34,6 +34,7 @@ def _no_tf32():
 @pytest.fixture(scope="module")
 def full():
     _no_tf32()
+    prev = torch.is_grad_enabled()
     torch.set_grad_enabled(False)
     ora = load_seeded(OracleUNet(**SD15_CONFIG).eval(), 0).to(DEV)
     mod = UNet2DConditionModel(**SD15_CONFIG)
@@ -42,6 +43,7 @@ def full():
     yield ora, mod
     del ora, mod
     torch.cuda.empty_cache()
+    torch.set_grad_enabled(prev)
 
 
 def _dev(inp):

@@ -20,6 +20,15 @@ DEV = "cuda"
 BF16 = torch.bfloat16
 
 
+@pytest.fixture(autouse=True)
+def _grad_enabled():
+    """other test modules switch autograd off globally; training needs it"""
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(True)
+    yield
+    torch.set_grad_enabled(prev)
+
+
 def _ref_attention(q, k, v, heads):
     n, nq, c = q.shape
     hd = c // heads
