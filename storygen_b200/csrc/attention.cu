@@ -465,8 +465,17 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
+          bool pf_done = true;
+          [[maybe_unused]] bool sf_done = true;
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
+            if (i == 16) {
+              // Probe the barriers this chunk needs at its end NOW (non-blocking test_wait, ~100+ clk of latency) and look at
+              // the answers after the remaining exps: a blocking try_wait at the point of use costs that latency every time,
+              // even when the phase completed long ago, and there are five such waits per tile.
+              pf_done = (j > 0) ? mbar_test(&p_free[tq * 4 + c], (j - 1) & 1) : true;
+              if constexpr (kHasNext) sf_done = (c == 0) ? mbar_test(&s_full[tq], (j + 1) & 1) : true;
+            }
             if constexpr (kHasNext) {
               if (c >= 1 && i == 16) {
                 // chunk c-1 of S(j+1) was requested a chunk ago: fold it into the next tile's row max
@@ -501,15 +510,15 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
                 tmem_st32(o_tmem + oc * 32, ov);
               }
             }
-            // the two k-steps of P V_{j-1} that read this chunk's columns of P have retired (issued ~a tile ago: no stall)
-            mbar_wait(&p_free[tq * 4 + c], (j - 1) & 1);
+            // the two k-steps of P V_{j-1} that read this chunk's columns of P have retired (issued ~a tile ago)
+            if (!pf_done) mbar_wait(&p_free[tq * 4 + c], (j - 1) & 1);
             tc_fence_after();
           }
           tmem_st16(p_tmem + c * 16, pk);
           if (kPingPong2 && c == kHandoff && !(tq == 1 && j == T - 1)) named_bar_arrive(2 - tq, 256);
           if constexpr (kHasNext) {
             if (c == 0) {
-              mbar_wait(&s_full[tq], (j + 1) & 1);
+              if (!sf_done) mbar_wait(&s_full[tq], (j + 1) & 1);
               tc_fence_after();
               SG_TS(1);
             }
