@@ -51,6 +51,13 @@ constexpr bool kPingPong2 = SG_ATTN2_PINGPONG != 0;
 #endif
 // bit (i % 8) set: pair i of a 32-column chunk takes both exps on the FMA pipe (0x11 = 1 in 4, 0x49 = 3 in 8, 0x55 = 1 in 2)
 constexpr unsigned kPolyMask2 = SG_ATTN2_POLY_MASK;
+#ifndef SG_ATTN2_SKEW
+#define SG_ATTN2_SKEW 2
+#endif
+// one-time phase offset between the two softmax warpgroups: group 1 starts its first tile's exps when group 0 has issued
+// chunk (kSkew2 - 1) of its first tile (0 = no offset), so that one group's per-tile tail (P publish, TMEM round trips, row
+// max reduction: no MUFU work) falls into the other group's exp phase instead of both idling the exp unit together
+constexpr int kSkew2 = SG_ATTN2_SKEW;
 constexpr int kPolyEvery = SG_ATTN_POLY_EVERY;  // 0 = all exps on MUFU; 4 = 1 in 4 on the FMA pipe; 2 = 1 in 2  // the other warpgroup may start its exps once chunk kHandoff (of 4) is issued
 
 struct AttnKParams {
@@ -461,6 +468,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
                                            make_float2(0.f, 0.f)};
         max_reset();
         if (kPingPong2) named_bar_sync(1 + tq, 256);
+        if (kSkew2 > 0 && j == 0 && tq == 1) named_bar_sync(3, 256);
         SG_TS(4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -516,6 +524,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
           }
           tmem_st16(p_tmem + c * 16, pk);
           if (kPingPong2 && c == kHandoff && !(tq == 1 && j == T - 1)) named_bar_arrive(2 - tq, 256);
+          if (kSkew2 > 0 && j == 0 && tq == 0 && c == kSkew2 - 1) named_bar_arrive(3, 256);
           if constexpr (kHasNext) {
             if (c == 0) {
               if (!sf_done) mbar_wait(&s_full[tq], (j + 1) & 1);

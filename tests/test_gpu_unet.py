@@ -189,3 +189,44 @@ def test_multi_image_condition_stage_matches_reference_golden(tiny):
     assert len(lat) == len(g["latents_step"])
     for got, ref in zip(lat, g["latents_step"]):
         check(got, ref, rel=0.15, what="multi-image-condition latents")
+
+
+def test_inference_script_flow_with_the_two_imports_swapped(tmp_path, tiny):
+    """The call sequence of the reference's inference.py (:42-120) against this package, with stub tokenizer / CLIP / VAE
+    and a tiny UNet checkpoint written in the diffusers directory layout: from_pretrained(subfolder="unet"),
+    enable_xformers_memory_efficient_attention(), `.to(device, dtype=torch.float16)` (:72-74), one CUDA generator per
+    sample (:95-99), the keyword call of `pipeline(...)` (:103-115) and `image[0].save(...)` on every entry of `.images`
+    (:117-120: `.images` is a list of per-image lists)."""
+    from oracle.stubs import StubTextEncoder, StubTokenizer, StubVAE
+    from oracle.make_golden import pipeline_images
+    ora, _ = tiny
+    ckpt = tmp_path / "ckpt"
+    src = UNet2DConditionModel(**TINY_CONFIG)
+    src.load_state_dict(ora.state_dict())
+    src.save_pretrained(str(ckpt / "unet"))
+    unet = UNet2DConditionModel.from_pretrained(str(ckpt), subfolder="unet")
+    vae, text_encoder, tokenizer = StubVAE(), StubTextEncoder(TINY_CONFIG["cross_attention_dim"]), StubTokenizer()
+    pipeline = StableDiffusionPipeline(vae=vae, text_encoder=text_encoder, tokenizer=tokenizer, unet=unet, scheduler=DDIMScheduler())
+    pipeline.enable_xformers_memory_efficient_attention()
+    weight_dtype = torch.float16
+    vae.to(DEV, dtype=weight_dtype)
+    text_encoder.to(DEV, dtype=weight_dtype)
+    unet.to(DEV, dtype=weight_dtype)
+    vae.eval(); text_encoder.eval(); unet.eval()
+    num_sample_per_prompt = 2
+    generator = []
+    for seed in (11, 222):
+        gen = torch.Generator(device=DEV)
+        gen.manual_seed(seed)
+        generator.append(gen)
+    ref_images = pipeline_images(5).float()  # (1, 2, 3, 512, 512), two prior frames
+    with torch.no_grad():
+        output = pipeline(stage="auto-regressive", prompt="The white cat is running after the black-haired man.",
+                          image_prompt=ref_images, prev_prompt=["The black-haired man", "The white cat."], height=512, width=512,
+                          generator=generator, num_inference_steps=3, guidance_scale=7, image_guidance_scale=3.5,
+                          num_images_per_prompt=num_sample_per_prompt).images
+    assert len(output) == num_sample_per_prompt
+    for i, image in enumerate(output):
+        image[0].save(str(tmp_path / f"{i}_output.png"))
+        assert image[0].size == (512, 512)
+    assert (tmp_path / "1_output.png").exists()
