@@ -52,12 +52,18 @@ constexpr bool kPingPong2 = SG_ATTN2_PINGPONG != 0;
 // bit (i % 8) set: pair i of a 32-column chunk takes both exps on the FMA pipe (0x11 = 1 in 4, 0x49 = 3 in 8, 0x55 = 1 in 2)
 constexpr unsigned kPolyMask2 = SG_ATTN2_POLY_MASK;
 #ifndef SG_ATTN2_SKEW
-#define SG_ATTN2_SKEW 2
+#define SG_ATTN2_SKEW 0
 #endif
 // one-time phase offset between the two softmax warpgroups: group 1 starts its first tile's exps when group 0 has issued
 // chunk (kSkew2 - 1) of its first tile (0 = no offset), so that one group's per-tile tail (P publish, TMEM round trips, row
 // max reduction: no MUFU work) falls into the other group's exp phase instead of both idling the exp unit together
 constexpr int kSkew2 = SG_ATTN2_SKEW;
+#ifndef SG_ATTN2_ORDERED
+#define SG_ATTN2_ORDERED 0
+#endif
+// 1: the exp loop of a chunk is written as an explicit 3-stage software pipeline (scale pair i+2 | exp pair i | pack pair i-1)
+// of order-preserving asm statements, so MUFU and FMA/ALU instructions alternate finely instead of in ptxas' bursts
+constexpr bool kOrdered2 = SG_ATTN2_ORDERED != 0;
 constexpr int kPolyEvery = SG_ATTN_POLY_EVERY;  // 0 = all exps on MUFU; 4 = 1 in 4 on the FMA pipe; 2 = 1 in 2  // the other warpgroup may start its exps once chunk kHandoff (of 4) is issued
 
 struct AttnKParams {
@@ -475,6 +481,35 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
           uint32_t pk[16];
           bool pf_done = true;
           [[maybe_unused]] bool sf_done = true;
+          if constexpr (kOrdered2 && Cfg::kSumTC) {
+            float2 xq[16], eq[16];
+            xq[0] = ffma2_o(make_float2(__uint_as_float(sv[c][0]), __uint_as_float(sv[c][1])), sc2, nm2);
+            xq[1] = ffma2_o(make_float2(__uint_as_float(sv[c][2]), __uint_as_float(sv[c][3])), sc2, nm2);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              if (t == 8) {
+                pf_done = (j > 0) ? mbar_test(&p_free[tq * 4 + c], (j - 1) & 1) : true;
+                if constexpr (kHasNext) sf_done = (c == 0) ? mbar_test(&s_full[tq], (j + 1) & 1) : true;
+                if constexpr (kHasNext) {
+                  if (c >= 1) {
+                    tmem_ld_wait();
+                    if constexpr (kMaskNext) mask_chunk(sv[c - 1], c - 1, valid_next);
+                    max_chunk(sv[c - 1]);
+                  }
+                }
+              }
+              if (t + 2 < 16)
+                xq[t + 2] = ffma2_o(make_float2(__uint_as_float(sv[c][2 * t + 4]), __uint_as_float(sv[c][2 * t + 5])), sc2, nm2);
+              if ((kPolyMask2 >> (t & 7)) & 1u) {
+                eq[t] = exp2_fma2(xq[t]);
+              } else {
+                eq[t].x = fast_exp2_o(xq[t].x);
+                eq[t].y = fast_exp2_o(xq[t].y);
+              }
+              if (t >= 1) pk[t - 1] = pack_bf16x2_o(eq[t - 1].x, eq[t - 1].y);
+            }
+            pk[15] = pack_bf16x2_o(eq[15].x, eq[15].y);
+          } else {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             if (i == 16) {
@@ -502,6 +537,7 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
             }
             if constexpr (!Cfg::kSumTC) sum2[(i >> 1) & 3] = fadd2(sum2[(i >> 1) & 3], e);
             pk[i >> 1] = pack_bf16x2(e.x, e.y);
+          }
           }
           if (j > 0) {
             if (c == 0 && __any_sync(0xffffffffu, need)) {

@@ -486,6 +486,33 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// "Ordered" variants: asm volatile statements keep their relative program order through ptxas, which lets a loop body fix
+// the interleave of MUFU / FMA / conversion instructions (an in-order warp blocked on a full MUFU queue cannot issue the
+// independent FMA work behind it, so bursts of either kind idle the other pipe).
+__device__ __forceinline__ float fast_exp2_o(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 ffma2_o(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm volatile("{\n"
+      ".reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %5};\n"
+      "mov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_o(float lo, float hi) {
+  uint32_t r;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // Packed fp32 pairs (sm_100 FFMA2 / FADD2): two IEEE fp32 results per lane for one issue slot.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   float2 d;
