@@ -59,7 +59,7 @@ constexpr unsigned kPolyMask2 = SG_ATTN2_POLY_MASK;
 // max reduction: no MUFU work) falls into the other group's exp phase instead of both idling the exp unit together
 constexpr int kSkew2 = SG_ATTN2_SKEW;
 #ifndef SG_ATTN2_ORDERED
-#define SG_ATTN2_ORDERED 0
+#define SG_ATTN2_ORDERED 1
 #endif
 // 1: the exp loop of a chunk is written as an explicit 3-stage software pipeline (scale pair i+2 | exp pair i | pack pair i-1)
 // of order-preserving asm statements, so MUFU and FMA/ALU instructions alternate finely instead of in ptxas' bursts
