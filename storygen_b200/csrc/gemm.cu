@@ -181,17 +181,9 @@ __device__ __forceinline__ void gemm_kernel_impl(const GemmKParams& p) {
       const int mt = (tile / p.num_n_tiles) * CG + cta_rank;
       const int nt = tile % p.num_n_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      // the tile after this one (its bias / csum / LayerNorm values are requested while this one is processed)
-      const int ntile = tile + item_step;
-      int nmt = -1, nnt = 0;
-      if (ntile < num_tiles) {
-        nmt = (ntile / p.num_n_tiles) * CG + cta_rank;
-        nnt = ntile % p.num_n_tiles;
-        if (CG == 2 && nmt >= num_m_tiles) nmt = -1;
-      }
       if (CG == 1 || mt < num_m_tiles) {
         epilogue_tile<BN, MODE, RT, CG>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase, est,
-                                        &res_bar[warp - 2], nmt, nnt, tile_ord, warp);
+                                        &res_bar[warp - 2], tile_ord, warp);
       } else {
         mbar_wait(&tfull_bar[acc], acc_phase);  // odd M-tile count: the pair's second half has no rows
       }

@@ -110,11 +110,6 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
 struct EpiState {
   uint32_t store_seq = 0;
   uint32_t res_phase = 0;  // RT = 1: parity of this warp's residual barrier
-  // values of the NEXT tile, requested while the current one is processed (their global-load latency would otherwise
-  // be exposed at every tile start: the epilogue is the critical path of the small-K GEMMs)
-  bool primed = false;
-  float nb_bias[4], nb_csum[4];
-  float nb_ln_s = 0.f, nb_ln_q = 0.f;
 };
 
 // One output tile of the epilogue, executed by one epilogue warp (quarter = TMEM lane quarter it may access = rows
@@ -134,8 +129,7 @@ template <int BN, int MODE, int RT, int CG = 1>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt, const int nt, const uint32_t t_row,
                                               uint8_t* scratch, const int quarter, const int grp, const int lane,
                                               uint64_t* tfull, const uint32_t tfull_phase, EpiState& st, uint64_t* res_bar,
-                                              const int next_mt, const int next_nt, const int tile_ord = 0,
-                                              const int warp_id = 0) {
+                                              const int tile_ord = 0, const int warp_id = 0) {
   using Cfg = GemmCfg<BN, RT, CG>;
   static_assert(RT == 0 || MODE == SG_EPI_LINEAR, "TMA residual slabs: LINEAR epilogue only");
   const bool dbg_on = (p.dbg != nullptr) && blockIdx.x == 0 && lane == 0 && tile_ord < 8;
@@ -200,51 +194,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
     }
   }
   if constexpr (MODE == SG_EPI_LINEAR && RT == 0) fetch_res(0, res[0]);
-  // bias / csum vectors of this warp's chunks and this row's LayerNorm partial sums: taken from the registers the previous
-  // tile's call requested them into (first tile: fetched here), then the NEXT tile's are requested
-  auto fetch_vectors = [&](const int f_mt, const int f_nt) {
-#pragma unroll
-    for (int ci = 0; ci < kMine; ++ci) {
-      const int col0 = f_nt * BN + (grp + 2 * ci) * 32;
-      const bool ok = (grp + 2 * ci < kChunks) && (col0 < p.N);
-      st.nb_bias[ci] = (p.bias != nullptr && ok) ? __ldg(p.bias + col0 + lane) : 0.f;
-      st.nb_csum[ci] = (use_ln && ok) ? __ldg(p.ln_csum + col0 + lane) : 0.f;
-    }
-    st.nb_ln_s = st.nb_ln_q = 0.f;
-    if (use_ln) {
-      const int ftx = f_mt % p.tiles_x, fty = (f_mt / p.tiles_x) % p.tiles_y, ftn = f_mt / (p.tiles_x * p.tiles_y);
-      const int fx = ftx * p.bw + (r & (p.bw - 1));
-      const int fy = fty * p.bh + ((r >> p.bw_log2) & (p.bh - 1));
-      const int fn = ftn * p.bn + (r >> (p.bw_log2 + p.bh_log2));
-      if ((fx < p.out_w) && (fy < p.out_h) && (fn < p.out_n)) {
-        const long long fm = (static_cast<long long>(fn) * p.out_h + fy) * p.out_w + fx;
-        for (int pp = 0; pp < p.ln_parts; ++pp) {
-          const float2 e = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(pp) * p.M + fm);
-          st.nb_ln_s += e.x;
-          st.nb_ln_q += e.y;
-        }
-      }
-    }
-  };
-  if (!st.primed) {
-    fetch_vectors(mt, nt);
-    st.primed = true;
-  }
-  // previous tile's readers of the smem vectors are done (they finished the tile before arriving on tempty / looping here)
+  // previous tile's readers of the vectors are done (they finished the tile before arriving on tempty / looping here)
   __syncwarp();
 #pragma unroll
   for (int ci = 0; ci < kMine; ++ci) {
-    if (p.bias != nullptr) sts32(bias_u32 + ci * 128 + lane * 4, __float_as_uint(st.nb_bias[ci]));
-    if (use_ln) sts32(csum_u32 + ci * 128 + lane * 4, __float_as_uint(st.nb_csum[ci]));
+    const int col0 = nt * BN + (grp + 2 * ci) * 32;
+    const bool ok = (grp + 2 * ci < kChunks) && (col0 < p.N);
+    if (p.bias != nullptr) sts32(bias_u32 + ci * 128 + lane * 4, ok ? __float_as_uint(__ldg(p.bias + col0 + lane)) : 0u);
+    if (use_ln) sts32(csum_u32 + ci * 128 + lane * 4, ok ? __float_as_uint(__ldg(p.ln_csum + col0 + lane)) : 0u);
   }
   float ln_mean = 0.f, ln_rstd = 1.f;
   if (use_ln && row_ok) {
     // fused LayerNorm of the A operand: mean / rstd of this thread's row from the producer's row partials
-    ln_mean = st.nb_ln_s * p.ln_inv_k;
-    ln_rstd = rsqrtf(fmaxf(st.nb_ln_q * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
+    float s = 0.f, q = 0.f;
+    for (int pp = 0; pp < p.ln_parts; ++pp) {
+      const float2 e = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + static_cast<long long>(pp) * p.M + m);
+      s += e.x;
+      q += e.y;
+    }
+    ln_mean = s * p.ln_inv_k;
+    ln_rstd = rsqrtf(fmaxf(q * p.ln_inv_k - ln_mean * ln_mean, 0.f) + p.ln_eps);
   }
   __syncwarp();
-  if (next_mt >= 0) fetch_vectors(next_mt, next_nt);  // in flight during this tile; first used at the next tile's start
   float2 rs2_acc = make_float2(0.f, 0.f), rq2_acc = make_float2(0.f, 0.f);  // per-row (sum, sumsq) of this warp's columns
   bool res_waited = false;
 
