@@ -124,7 +124,7 @@ typedef struct sg_gemm_args {
 } sg_gemm_args;
 
 int sg_gemm(const sg_gemm_args* args, void* stream);
-/* number of row-statistics partials sg_gemm(args) writes per row (2 x its N tiles; depends on N and the tile grid) */
+/* number of row-statistics partials sg_gemm(args) writes per row (epilogue warpgroups x N tiles; depends on N, K and the tile grid) */
 int sg_gemm_row_stat_parts(const sg_gemm_args* args);
 
 /* ---- fused attention core (FlashAttention-style, tcgen05 + TMEM) -----------------------------

@@ -64,6 +64,11 @@ constexpr int kSkew2 = SG_ATTN2_SKEW;
 // 1: the exp loop of a chunk is written as an explicit 3-stage software pipeline (scale pair i+2 | exp pair i | pack pair i-1)
 // of order-preserving asm statements, so MUFU and FMA/ALU instructions alternate finely instead of in ptxas' bursts
 constexpr bool kOrdered2 = SG_ATTN2_ORDERED != 0;
+#ifndef SG_ATTN_MC_POLY_MASK
+#define SG_ATTN_MC_POLY_MASK 0x1
+#endif
+// attn_mc_kernel: bit b set = pair b of every 4 column pairs takes the packed cubic on the FMA pipe instead of MUFU.EX2
+constexpr unsigned kMcPolyMask = SG_ATTN_MC_POLY_MASK;
 constexpr int kPolyEvery = SG_ATTN_POLY_EVERY;  // 0 = all exps on MUFU; 4 = 1 in 4 on the FMA pipe; 2 = 1 in 2  // the other warpgroup may start its exps once chunk kHandoff (of 4) is issued
 
 struct AttnKParams {
@@ -785,6 +790,296 @@ __global__ void __launch_bounds__(AttnCfg<D, QT, SHORT>::kThreads, AttnCfg<D, QT
   }
 }
 
+// =================================================================================================================
+// attn_mc_kernel: the "many small CTAs" form of the core for head dims < 64 (d = 40 / 32: the 64x64-latent level, 5/6 of
+// the attention time of a step).
+//
+// With d = 40 a 128 x 128 score tile costs the tensor core ~350 clk but the exp unit 1024 (16 exp2 / clk / SM) and the
+// softmax warps ~600 issue slots each: the loop is bound by how well the softmax instruction streams of ONE sub-partition
+// overlap each other's latencies (TMEM round trips, MUFU queue, barrier wake-ups).  attn_kernel<40, 2> keeps 2 softmax warps
+// per sub-partition (two query tiles of one CTA) and measures 0.60 exp-unit utilisation however its loop is scheduled
+// (profiles/r02_attn_variants.log).  This kernel shrinks the CTA instead: ONE 128-query tile, 64-key tiles, S (64 columns)
+// with P written over it in place and O (d + ones column -> 48 columns) in 128 TMEM columns, Q + a 4-slot ring of 8 KB
+// K / V tiles in 49 KB of shared memory, 8 warps with 96 registers for the 4 softmax warps -- so FOUR CTAs share an SM:
+// 4 softmax warps per sub-partition, each from an independent CTA at an independent point of its loop, and the
+// hardware scheduler does the interleaving the two-tile kernel tried to do by hand.
+//   warp 0: TMA (Q once; K_j, V_j through the ring)        warp 1: tcgen05 issuer (QK_j -> S; PV_j: O += P V_j)
+//   warp 2: writes the ones column into every V tile       warps 4-7: online softmax, thread = query row
+// Per tile and CTA the chain is serial (S_j -> softmax -> P_j -> PV_j, QK_{j+1} -> S_{j+1}); the other three CTAs fill
+// the gaps.  The row sum comes from the tensor core (ones column of V, as in attn_kernel), the rescale of O is lazy.
+// =================================================================================================================
+template <int D>
+struct AttnMcCfg {
+  static_assert(D < 64 && D % 8 == 0, "one 64-channel atom with room for the ones column");
+  static constexpr int KQ = (D + 15) / 16;            // k-steps of Q K^T
+  static constexpr int kNPV = (D + 16) & ~15;         // head channels + the ones column, UMMA N granularity
+  static constexpr int kOnesChunk = D / 8;            // 16-byte chunk of a V row that holds channel D
+  static constexpr int kTK = 64;                      // keys per tile
+  static constexpr int kQBytes = 128 * 128;           // [128 queries x 64 channels] swizzle 128B
+  static constexpr int kKvBytes = kTK * 128;          // [64 keys x 64 channels]
+  static constexpr int kSlots = 4;                    // ring order K0 V0 K1 V1 ...
+  static constexpr int kThreads = 256;
+  static constexpr int kCtasPerSm = 4;
+  static constexpr int kColO = 64;                    // S / P at column 0
+  static constexpr int kTmemCols = 128;
+  static constexpr int kSmemBytes = kQBytes + kSlots * kKvBytes + 1024 + 256;
+  static_assert(kColO + kNPV <= kTmemCols, "S + O must fit 128 TMEM columns");
+};
+
+template <int D>
+__global__ void __launch_bounds__(AttnMcCfg<D>::kThreads, AttnMcCfg<D>::kCtasPerSm)
+    attn_mc_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = AttnMcCfg<D>;
+  constexpr int kSlots = Cfg::kSlots;
+  constexpr int TK = Cfg::kTK;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* kv_smem = smem + Cfg::kQBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + kSlots * Cfg::kKvBytes);
+  uint64_t* kv_full = bars;                  // [kSlots] TMA -> MMA / V fixer
+  uint64_t* kv_empty = bars + kSlots;        // [kSlots] MMA -> TMA
+  uint64_t* v_ready = bars + 2 * kSlots;     // [kSlots] V fixer -> MMA
+  uint64_t* q_full = bars + 3 * kSlots;      // TMA -> softmax warps
+  uint64_t* q_ready = q_full + 1;            // softmax warps -> MMA (Q pad zeroed)
+  uint64_t* s_full = q_full + 2;             // MMA -> softmax: S_j complete (and P V_{j-1} retired)
+  uint64_t* p_full = q_full + 3;             // softmax -> MMA: P_j published
+  uint64_t* o_done = q_full + 4;             // MMA -> softmax: last P V retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 5);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int T = (p.nk + TK - 1) / TK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&v_ready[i], 1);
+    }
+    mbar_init(q_full, 1);
+    mbar_init(q_ready, 4);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  auto slot_of = [](int i) { return i % kSlots; };
+  auto phase_of = [](int i) { return static_cast<uint32_t>((i / kSlots) & 1); };
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == 0) {
+      // ===================== TMA loader =====================
+      const int kv_img = (p.kv_map != nullptr) ? p.kv_map[img] : img;
+      mbar_arrive_expect_tx_w(q_full, Cfg::kQBytes);
+      tma_load_3d_w(q_smem, &p.q_map, q_full, head * D, q0, img);
+      for (int i = 0; i < 2 * T; ++i) {
+        const int slot = slot_of(i);
+        mbar_wait(&kv_empty[slot], phase_of(i) ^ 1);
+        mbar_arrive_expect_tx_w(&kv_full[slot], Cfg::kKvBytes);
+        tma_load_3d_w(kv_smem + slot * Cfg::kKvBytes, (i & 1) ? &p.v_map : &p.k_map, &kv_full[slot], head * D,
+                      (i >> 1) * TK, kv_img);
+      }
+    } else if (warp == 1) {
+      // ===================== tcgen05 issuer =====================
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, TK, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, Cfg::kNPV, 0, 1);  // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(q_smem);
+      auto tile_addr = [&](int i) { return smem_u32(kv_smem + slot_of(i) * Cfg::kKvBytes); };
+      auto qk = [&](int i) {
+        mbar_wait(&kv_full[slot_of(i)], phase_of(i));
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KQ; ++ks)
+          umma_ss_w(tmem_base, make_smem_desc(q_addr + ks * 32, 16, 1024, kLayoutSW128),
+                    make_smem_desc(tile_addr(i) + ks * 32, 16, 1024, kLayoutSW128), idesc_qk, ks != 0);
+        umma_commit_w(&kv_empty[slot_of(i)]);
+        umma_commit_w(s_full);
+      };
+      mbar_wait(q_ready, 0);
+      qk(0);
+      for (int j = 0; j < T; ++j) {
+        const int iv = 2 * j + 1;
+        mbar_wait(&v_ready[slot_of(iv)], phase_of(iv));
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < TK / 16; ++ks)  // 16 keys per k-step: 8 TMEM columns of P, 2048 B of the V tile
+          umma_ts_w(tmem_base + Cfg::kColO, tmem_base + ks * 8,
+                    make_smem_desc(tile_addr(iv) + ks * 2048, kAtomBytes, 1024, kLayoutSW128), idesc_pv,
+                    !(j == 0 && ks == 0));
+        umma_commit_w(&kv_empty[slot_of(iv)]);
+        if (j + 1 < T) qk(iv + 1);  // overwrites P_j: the tensor pipe executes in issue order
+        else umma_commit_w(o_done);
+      }
+    } else if (warp == 2) {
+      // ===================== V fixer: ones into channel D of every V tile (row sums on the tensor core) =====================
+      const uint4 ones = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);  // 8 x bf16 1.0
+      for (int j = 0; j < T; ++j) {
+        const int iv = 2 * j + 1, slot = slot_of(iv);
+        mbar_wait(&kv_full[slot], phase_of(iv));
+        const uint32_t tile = smem_u32(kv_smem + slot * Cfg::kKvBytes);
+#pragma unroll
+        for (int rr = 0; rr < TK / 32; ++rr) {
+          const int row = rr * 32 + lane;
+          sts128(tile + row * 128 + ((Cfg::kOnesChunk ^ (row & 7)) << 4), ones);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&v_ready[slot]);
+      }
+    }
+  } else {
+    // ===================== online softmax: thread = query row =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row within the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_base;
+    const uint32_t o_tmem = tmem_base + lane_base + Cfg::kColO;
+
+    mbar_wait(q_full, 0);
+    if constexpr (D % 16 != 0) {
+      // zero Q channels [D, D+8): Q K^T runs over KQ * 16 channels, K's channels there belong to the next head
+      uint4* dst = reinterpret_cast<uint4*>(q_smem + r * 128 + (((D / 8) ^ (r & 7)) << 4));
+      *dst = make_uint4(0, 0, 0, 0);
+      fence_proxy_async_smem();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(q_ready);
+
+    float m_used = 0.f;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+    // one 64-key tile; kMasked is only instantiated for the LAST tile (ragged nk), so the mask stays out of the steady state
+    auto tile = [&](const int j, auto masked_tag) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
+      uint32_t sv[2][32];
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      tmem_ld32(s_tmem, sv[0]);
+      tmem_ld32(s_tmem + 32, sv[1]);
+      tmem_ld_wait();
+      if constexpr (kMasked) {
+        const int valid = p.nk - j * TK;  // keys valid in the last tile (>= 1)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;  // -inf
+      }
+      float mx8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(__uint_as_float(sv[0][i]), __uint_as_float(sv[1][i]));
+#pragma unroll
+      for (int i = 8; i < 32; ++i)
+        mx8[i & 7] = fmaxf(mx8[i & 7], fmaxf(__uint_as_float(sv[0][i]), __uint_as_float(sv[1][i])));
+      const float mt = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                             fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
+      // lazy rescale: O (and its ones column = the running row sum) is only rescaled when the maximum grew by > 2^8
+      bool need = false;
+      float alpha = 1.f;
+      if (j == 0) {
+        m_used = mt;
+      } else if (mt > m_used + 8.f) {
+        alpha = fast_exp2(m_used - mt);
+        m_used = mt;
+        need = true;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        // S_j complete implies P V_{j-1} retired (issue order), so O is quiescent; 16 columns at a time (register budget)
+#pragma unroll 1
+        for (int c = 0; c < Cfg::kNPV / 16; ++c) {
+          uint32_t ow[16];
+          tmem_ld16(o_tmem + c * 16, ow);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ow[i] = __float_as_uint(__uint_as_float(ow[i]) * alpha);
+          tmem_st16(o_tmem + c * 16, ow);
+        }
+      }
+      const float2 nm2 = make_float2(-m_used, -m_used);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 x = ffma2(make_float2(__uint_as_float(sv[c][i]), __uint_as_float(sv[c][i + 1])), sc2, nm2);
+          // the exp unit bounds the loop: the pairs selected by kMcPolyMask run as a packed cubic on the FMA pipe
+          float2 e;
+          if ((kMcPolyMask >> ((i >> 1) & 3)) & 1u) e = exp2_fma2(x);
+          else e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+          pk[i >> 1] = pack_bf16x2(e.x, e.y);
+        }
+        tmem_st16(s_tmem + c * 16, pk);  // P_j over S_j (this thread's row only; all of S_j is in registers)
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    };
+    for (int j = 0; j + 1 < T; ++j) tile(j, std::false_type{});
+    if (p.nk % TK != 0) tile(T - 1, std::true_type{});
+    else tile(T - 1, std::false_type{});
+
+    // final: O / l -> global (only the d valid channels of this head)
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    const float l_run = __uint_as_float(tmem_ld1(o_tmem + D));  // column D of O = sum_k P[:, k]
+    tmem_ld_wait();
+    const float inv_l = 1.0f / l_run;
+    const int q = q0 + r;
+    if (p.lse != nullptr && q < p.nq)
+      p.lse[(static_cast<long long>(img) * p.n_heads + head) * p.nq + q] = m_used + log2f(l_run);
+    bf16* orow = p.o + static_cast<long long>(img) * p.o_stride_n + static_cast<long long>(q) * p.o_stride_t + head * D;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      if (c * 32 < D) {
+        uint32_t ov[32];
+        if (c == 0) {
+          tmem_ld32(o_tmem, ov);
+        } else {
+          uint32_t ow[16];
+          tmem_ld16(o_tmem + 32, ow);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ov[i] = ow[i];
+        }
+        tmem_ld_wait();
+        if (q < p.nq) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (c * 32 + g * 8 < D) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(ov[8 * g + 0]) * inv_l, __uint_as_float(ov[8 * g + 1]) * inv_l);
+              w.y = pack_bf16x2(__uint_as_float(ov[8 * g + 2]) * inv_l, __uint_as_float(ov[8 * g + 3]) * inv_l);
+              w.z = pack_bf16x2(__uint_as_float(ov[8 * g + 4]) * inv_l, __uint_as_float(ov[8 * g + 5]) * inv_l);
+              w.w = pack_bf16x2(__uint_as_float(ov[8 * g + 6]) * inv_l, __uint_as_float(ov[8 * g + 7]) * inv_l);
+              *reinterpret_cast<uint4*>(orow + c * 32 + g * 8) = w;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 template <int D, int QT, bool DBG = false, bool SHORT = false>
 static int launch_attn(const AttnKParams& kp, int nq, int heads, int lanes, cudaStream_t stream) {
   using Cfg = AttnCfg<D, QT, SHORT>;
@@ -801,9 +1096,36 @@ static int launch_attn(const AttnKParams& kp, int nq, int heads, int lanes, cuda
   return static_cast<int>(cudaGetLastError());
 }
 
+template <int D>
+static int launch_attn_mc(const AttnKParams& kp, int nq, int heads, int lanes, cudaStream_t stream) {
+  using Cfg = AttnMcCfg<D>;
+  static std::atomic<uint64_t> configured{0};
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_mc_kernel<D>), Cfg::kSmemBytes, &configured)) return rc;
+  dim3 grid((nq + 127) / 128, heads, lanes);
+  attn_mc_kernel<D><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+// attn_mc_kernel is OPT-IN (SG_ATTN_MC=1).  Timed alone in short bursts (1965 MHz) it is 9 % faster than attn_kernel<40, 2>
+// (1254 vs 1383 SM-clk per 128 x 128 tile, profiles/r02_attn_mc_bench.log); but a denoising step runs at the board's power
+// cap, and there the joules per launch decide: 1.39 J at 1725 MHz against 1.35 J at 1880 MHz for the two-tile kernel in a
+// sustained loop (profiles/r02_attn_power.log: twice the K / V traffic from L2, narrower MMAs), i.e. 3 % SLOWER, and the step
+// time of bench.py is unchanged.  The two-tile kernel stays the default.
+static bool use_attn_mc(int head_dim, int nk) {
+  static const bool enabled = [] {
+    const char* e = getenv("SG_ATTN_MC");
+    return e != nullptr && e[0] == '1';
+  }();
+  return enabled && (head_dim == 40 || head_dim == 32) && nk > 128;
+}
+
 // two query tiles per CTA whenever there are at least two (and the head dim leaves TMEM room)
 template <int D>
 static int launch_attn_auto(const AttnKParams& kp, int nq, int heads, int lanes, cudaStream_t stream) {
+  if constexpr (D < 64) {
+    if (use_attn_mc(D, kp.nk)) return launch_attn_mc<D>(kp, nq, heads, lanes, stream);
+  }
   if constexpr (D <= 128) {
     if (kp.nk <= 128) return launch_attn<D, 1, false, true>(kp, nq, heads, lanes, stream);  // text cross-attention
     if (nq > 128) return launch_attn<D, 2>(kp, nq, heads, lanes, stream);
@@ -812,11 +1134,11 @@ static int launch_attn_auto(const AttnKParams& kp, int nq, int heads, int lanes,
 }
 
 static int make_tok_map(CUtensorMap* m, const void* ptr, int channels, int tokens, int lanes, int64_t stride_t,
-                        int64_t stride_n) {
+                        int64_t stride_n, uint32_t box_tokens = 128) {
   uint64_t dims[3] = {static_cast<uint64_t>(channels), static_cast<uint64_t>(tokens),
                       static_cast<uint64_t>(lanes)};
   uint64_t strides[2] = {static_cast<uint64_t>(stride_t) * 2, static_cast<uint64_t>(stride_n) * 2};
-  uint32_t box[3] = {64, 128, 1};
+  uint32_t box[3] = {64, box_tokens, 1};
   return encode_tmap_bf16(m, ptr, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -838,8 +1160,9 @@ extern "C" int sg_attention(const sg_attn_args* a, void* stream_v) {
   memset(&kp, 0, sizeof(kp));
   int rc;
   if ((rc = make_tok_map(&kp.q_map, a->q, C, a->nq, a->n_lanes, a->q_stride_t, a->q_stride_n)) != 0) return rc;
-  if ((rc = make_tok_map(&kp.k_map, a->k, C, a->nk, kv_lanes, a->k_stride_t, a->k_stride_n)) != 0) return rc;
-  if ((rc = make_tok_map(&kp.v_map, a->v, C, a->nk, kv_lanes, a->v_stride_t, a->v_stride_n)) != 0) return rc;
+  const uint32_t kv_box = use_attn_mc(a->head_dim, a->nk) ? 64 : 128;  // keys per K / V tile of the kernel that will run
+  if ((rc = make_tok_map(&kp.k_map, a->k, C, a->nk, kv_lanes, a->k_stride_t, a->k_stride_n, kv_box)) != 0) return rc;
+  if ((rc = make_tok_map(&kp.v_map, a->v, C, a->nk, kv_lanes, a->v_stride_t, a->v_stride_n, kv_box)) != 0) return rc;
   kp.o = static_cast<bf16*>(a->o);
   kp.o_stride_n = a->o_stride_n;
   kp.o_stride_t = a->o_stride_t;

@@ -185,9 +185,10 @@ struct GnSrc {
   const float2* parts;
   int c, tiles_xy, bn, reps, m_tiles;
 };
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const GnSrc s0, const GnSrc s1, int hw, int groups, float eps,
-                                                          float2* __restrict__ mean_rstd) {
-  __shared__ double s_s[128], s_q[128];
+constexpr int kGnFinThreads = 256;
+__global__ void __launch_bounds__(kGnFinThreads) gn_finalize_kernel(const GnSrc s0, const GnSrc s1, int hw, int groups, float eps,
+                                                                    float2* __restrict__ mean_rstd) {
+  __shared__ double s_s[kGnFinThreads / 32], s_q[kGnFinThreads / 32];
   const int g = blockIdx.x, n = blockIdx.y;
   const int C = s0.c + s1.c, cpg = C / groups;
   const int ch_lo = g * cpg, ch_hi = ch_lo + cpg;
@@ -205,30 +206,43 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const GnSrc s0, const 
     const long long tile0 = static_cast<long long>(n / S.bn) * S.tiles_xy;
     const int per_rep = S.tiles_xy * nq * nch;
     const int items = S.reps * per_rep;
-    for (int it = threadIdx.x; it < items; it += 128) {
+    auto fetch = [&](const int it) {
+      if (it >= items) return make_float2(0.f, 0.f);
       const int rep = it / per_rep, r = it - rep * per_rep;
       const int ch = lo + r % nch;
       const int bi = r / nch;
       const long long blk = static_cast<long long>(rep) * S.m_tiles * 4 + (tile0 + bi / nq) * 4 + q0 + bi % nq;
-      const float2 e = __ldg(S.parts + blk * S.c + ch);
-      s += static_cast<double>(e.x);
-      q += static_cast<double>(e.y);
+      return __ldg(S.parts + blk * S.c + ch);
+    };
+    // the kernel is a chain of dependent L2 round trips: four independent loads in flight per thread
+    for (int it = threadIdx.x; it < items; it += 4 * kGnFinThreads) {
+      const float2 e0 = fetch(it), e1 = fetch(it + kGnFinThreads), e2 = fetch(it + 2 * kGnFinThreads),
+                   e3 = fetch(it + 3 * kGnFinThreads);
+      s += (static_cast<double>(e0.x) + static_cast<double>(e1.x)) + (static_cast<double>(e2.x) + static_cast<double>(e3.x));
+      q += (static_cast<double>(e0.y) + static_cast<double>(e1.y)) + (static_cast<double>(e2.y) + static_cast<double>(e3.y));
     }
   }
-  s_s[threadIdx.x] = s;
-  s_q[threadIdx.x] = q;
+  // fixed-order reduction: butterfly inside the warp, then the 8 warp sums in order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_s[threadIdx.x >> 5] = s;
+    s_q[threadIdx.x >> 5] = q;
+  }
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      s_s[threadIdx.x] += s_s[threadIdx.x + o];
-      s_q[threadIdx.x] += s_q[threadIdx.x + o];
-    }
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+#pragma unroll
+    for (int w = 0; w < kGnFinThreads / 32; ++w) {
+      ts += s_s[w];
+      tq += s_q[w];
+    }
     const double cnt = static_cast<double>(hw) * cpg;
-    const double mean = s_s[0] / cnt;
-    double var = s_q[0] / cnt - mean * mean;
+    const double mean = ts / cnt;
+    double var = tq / cnt - mean * mean;
     var = var > 0.0 ? var : 0.0;
     mean_rstd[static_cast<long long>(n) * groups + g] =
         make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps))));
@@ -590,7 +604,7 @@ extern "C" int sg_groupnorm_finalize(const sg_gn_parts* src0, const sg_gn_parts*
     C += p.c;
   }
   if (groups < 1 || C % groups || n_img < 1) return SG_ERR_SHAPE;
-  gn_finalize_kernel<<<dim3(groups, n_img), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  gn_finalize_kernel<<<dim3(groups, n_img), kGnFinThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       s[0], s[1], hw, groups, eps, reinterpret_cast<float2*>(mean_rstd));
   SG_LAUNCH_END();
 }

@@ -26,9 +26,10 @@ namespace sg {
 // with M = 256 and commits to the barriers of both CTAs, each CTA's epilogue drains its own 128 accumulator rows.  Per
 // k-block a CTA stages 16 KB + 64 B x BN instead of 16 KB + 128 B x BN: the operand ingest that bounds the K-heavy
 // convolutions (and a good part of their power) drops by a quarter to a third.
-template <int BN, int MODE, int RT, int CG>
+template <int BN, int MODE, int RT, int CG, int EG>
 __device__ __forceinline__ void gemm_kernel_impl(const GemmKParams& p) {
-  using Cfg = GemmCfg<BN, RT, CG>;
+  using Cfg = GemmCfg<BN, RT, CG, EG>;
+  constexpr int kEpiWarps = Cfg::kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -167,7 +168,7 @@ __device__ __forceinline__ void gemm_kernel_impl(const GemmKParams& p) {
   } else {
     // ===================== epilogue (see gemm_common.cuh::epilogue_tile) =====================
     const int quarter = warp & 3;     // TMEM lane quarter this warp may access
-    const int grp = (warp - 2) >> 2;  // epilogue warpgroup 0 / 1
+    const int grp = (warp - 2) >> 2;  // epilogue warpgroup 0 .. EG-1
     uint8_t* scratch = epi_scratch + (warp - 2) * Cfg::kWarpScratch;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -182,7 +183,7 @@ __device__ __forceinline__ void gemm_kernel_impl(const GemmKParams& p) {
       const int nt = tile % p.num_n_tiles;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
       if (CG == 1 || mt < num_m_tiles) {
-        epilogue_tile<BN, MODE, RT, CG>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase, est,
+        epilogue_tile<BN, MODE, RT, CG, EG>(p, mt, nt, t_row, scratch, quarter, grp, lane, &tfull_bar[acc], acc_phase, est,
                                         &res_bar[warp - 2], tile_ord, warp);
       } else {
         mbar_wait(&tfull_bar[acc], acc_phase);  // odd M-tile count: the pair's second half has no rows
@@ -213,40 +214,51 @@ __device__ __forceinline__ void gemm_kernel_impl(const GemmKParams& p) {
   }
 }
 
-template <int BN, int MODE, int RT>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_kernel(const __grid_constant__ GemmKParams p) {
-  gemm_kernel_impl<BN, MODE, RT, 1>(p);
+constexpr int kWideLinear = 3, kWideGeglu = 4;  // epilogue warpgroups of the small-K kernels (pick_epi_groups)
+
+template <int BN, int MODE, int RT, int EG>
+__global__ void __launch_bounds__(64 + 128 * EG, 1) gemm_kernel(const __grid_constant__ GemmKParams p) {
+  gemm_kernel_impl<BN, MODE, RT, 1, EG>(p);
 }
-template <int BN, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1) gemm_pair_kernel(const __grid_constant__ GemmKParams p) {
-  gemm_kernel_impl<BN, MODE, 0, 2>(p);
+template <int BN, int MODE, int EG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 128 * EG, 1) gemm_pair_kernel(const __grid_constant__ GemmKParams p) {
+  gemm_kernel_impl<BN, MODE, 0, 2, EG>(p);
 }
 
-template <int BN, int MODE, int RT = 0>
+template <int BN, int MODE, int RT = 0, int EG = 2>
 static int launch_gemm_mode(const GemmKParams& kp, int num_tiles, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, RT>;
+  using Cfg = GemmCfg<BN, RT, 1, EG>;
   static std::atomic<uint64_t> configured{0};
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<BN, MODE, RT>), Cfg::kSmemBytes, &configured)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_kernel<BN, MODE, RT, EG>), Cfg::kSmemBytes, &configured)) return rc;
   int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_kernel<BN, MODE, RT><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
+  gemm_kernel<BN, MODE, RT, EG><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, int EG = 2>
 static int launch_gemm_pair(const GemmKParams& kp, int num_pair_tiles, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, 0, 2>;
+  using Cfg = GemmCfg<BN, 0, 2, EG>;
   static std::atomic<uint64_t> configured{0};
-  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_pair_kernel<BN, MODE>), Cfg::kSmemBytes, &configured)) return rc;
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_pair_kernel<BN, MODE, EG>), Cfg::kSmemBytes, &configured)) return rc;
   const int pairs = num_sms() / 2;
   const int grid = 2 * (num_pair_tiles < pairs ? num_pair_tiles : pairs);
-  gemm_pair_kernel<BN, MODE><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(kp);
+  gemm_pair_kernel<BN, MODE, EG><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
   count_launch();
   return static_cast<int>(cudaGetLastError());
 }
 
+// eg > 2: the wide-epilogue instantiations (pick_epi_groups)
 template <int BN>
-static int launch_gemm(const GemmKParams& kp, int num_tiles, bool res_tma, cudaStream_t stream) {
+static int launch_gemm(const GemmKParams& kp, int num_tiles, bool res_tma, int eg, cudaStream_t stream) {
+  if constexpr (BN == 160) {
+    if (kp.mode == SG_EPI_LINEAR && eg == kWideLinear)
+      return res_tma ? launch_gemm_mode<BN, SG_EPI_LINEAR, 1, kWideLinear>(kp, num_tiles, stream)
+                     : launch_gemm_mode<BN, SG_EPI_LINEAR, 0, kWideLinear>(kp, num_tiles, stream);
+  }
+  if constexpr (BN == 256) {
+    if (kp.mode == SG_EPI_GEGLU && eg == kWideGeglu) return launch_gemm_mode<BN, SG_EPI_GEGLU, 0, kWideGeglu>(kp, num_tiles, stream);
+  }
   if constexpr (BN <= 160) {
     if (res_tma && kp.mode == SG_EPI_LINEAR) return launch_gemm_mode<BN, SG_EPI_LINEAR, 1>(kp, num_tiles, stream);
   }
@@ -274,6 +286,17 @@ static int pick_bn_tile(const sg_gemm_args* a) {
   return bn_tile;
 }
 
+// Epilogue warpgroups: the small-K GEMMs (K <= 1280: every Linear of the transformer blocks) are bound by the epilogue's
+// dependent chains, not by the main loop, and run with more than two epilogue warpgroups: three for the 160-wide LINEAR
+// tiles (5 chunks: 2 + 2 + 1), four for the 256-wide GEGLU tiles (8 chunks: 2 each).  Measured against two warpgroups
+// (profiles/r02_gemm_epi_groups.log): QKV projection 90 -> 75 us, GEGLU 188 -> 162 us, out-projection + residual 45 -> 40 us.
+static int pick_epi_groups(const sg_gemm_args* a, int bn_tile) {
+  if (a->Ktot > 1280) return 2;
+  if (bn_tile == 160 && a->mode == SG_EPI_LINEAR) return kWideLinear;
+  if (bn_tile == 256 && a->mode == SG_EPI_GEGLU) return kWideGeglu;
+  return 2;
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -281,7 +304,7 @@ using namespace sg;
 extern "C" int sg_gemm_row_stat_parts(const sg_gemm_args* a) {
   if (a == nullptr || a->bw < 1 || a->bh < 1 || a->bn < 1 || a->N < 1) return SG_ERR_ARG;
   const int bn_tile = pick_bn_tile(a);
-  return 2 * static_cast<int>((a->N + bn_tile - 1) / bn_tile);
+  return pick_epi_groups(a, bn_tile) * static_cast<int>((a->N + bn_tile - 1) / bn_tile);
 }
 
 extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
@@ -326,6 +349,7 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
   }
 
   const int bn_tile = pick_bn_tile(a);
+  const int eg = pick_epi_groups(a, bn_tile);
   {
     uint64_t dims[2] = {static_cast<uint64_t>(a->Ktot), static_cast<uint64_t>(a->N)};
     uint64_t strides[1] = {static_cast<uint64_t>(a->Ktot) * 2};
@@ -422,14 +446,18 @@ extern "C" int sg_gemm(const sg_gemm_args* a, void* stream_v) {
     uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(bn_tile / 2)};
     int rc = encode_tmap_bf16(&kp.b_map, a->b, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != 0) return rc;
-    if (a->mode == SG_EPI_GEGLU) return launch_gemm_pair<256, SG_EPI_GEGLU>(kp, num_pair_tiles, stream);
-    return bn_tile == 256 ? launch_gemm_pair<256, SG_EPI_LINEAR>(kp, num_pair_tiles, stream)
-                          : launch_gemm_pair<160, SG_EPI_LINEAR>(kp, num_pair_tiles, stream);
+    if (a->mode == SG_EPI_GEGLU) {
+      if (eg == kWideGeglu) return launch_gemm_pair<256, SG_EPI_GEGLU, kWideGeglu>(kp, num_pair_tiles, stream);
+      return launch_gemm_pair<256, SG_EPI_GEGLU>(kp, num_pair_tiles, stream);
+    }
+    if (bn_tile == 256) return launch_gemm_pair<256, SG_EPI_LINEAR>(kp, num_pair_tiles, stream);
+    if (eg == kWideLinear) return launch_gemm_pair<160, SG_EPI_LINEAR, kWideLinear>(kp, num_pair_tiles, stream);
+    return launch_gemm_pair<160, SG_EPI_LINEAR>(kp, num_pair_tiles, stream);
   }
   switch (bn_tile) {
-    case 256: return launch_gemm<256>(kp, num_tiles, false, stream);
-    case 160: return launch_gemm<160>(kp, num_tiles, res_tma, stream);
-    case 128: return launch_gemm<128>(kp, num_tiles, res_tma, stream);
-    default: return launch_gemm<64>(kp, num_tiles, res_tma, stream);
+    case 256: return launch_gemm<256>(kp, num_tiles, false, eg, stream);
+    case 160: return launch_gemm<160>(kp, num_tiles, res_tma, eg, stream);
+    case 128: return launch_gemm<128>(kp, num_tiles, res_tma, eg, stream);
+    default: return launch_gemm<64>(kp, num_tiles, res_tma, eg, stream);
   }
 }

@@ -7,8 +7,6 @@ namespace sg {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // one 128-byte swizzle atom of bf16
-constexpr int kGemmThreads = 320;  // TMA warp + MMA warp + 2 epilogue warpgroups
-constexpr int kEpiWarps = 8;
 
 
 struct GemmKParams {
@@ -38,7 +36,7 @@ struct GemmKParams {
   long long* dbg;  // bring-up aid: phase clocks of CTA 0 (NULL in production)
   // fused normalisation hooks (include/storygen_b200.h): all optional
   long long M;            // total output rows (stride of the row-statistics parts)
-  float* row_stats_out;   // [2 * num_n_tiles][M][2]
+  float* row_stats_out;   // [EG * num_n_tiles][M][2]  (sg_gemm_row_stat_parts)
   const float* ln_stats;  // [ln_parts][M][2]
   const float* ln_csum;   // [N]
   int ln_parts;
@@ -55,17 +53,22 @@ struct GemmKParams {
 //           the transformer blocks (K = C or 2C), whose epilogue is the critical path: a row-per-thread global read costs
 //           one L1 wavefront per 16 bytes, the bulk copy none.
 //   CG = 2: CTA pair (cta_group::2): this CTA stages only its half of the B tile.
-template <int BN, int RT = 0, int CG = 1>
+//   EG = number of epilogue warpgroups (2..4), warpgroup g taking the 32-column chunks g, g + EG, ...  Two suffice when the
+//           main loop is the critical path (K-heavy convolutions); the small-K GEMMs of the transformer blocks are bound by
+//           the epilogue's dependent chains (tcgen05.ld -> arithmetic -> shared -> TMA store), which more resident warps hide.
+template <int BN, int RT = 0, int CG = 1, int EG = 2>
 struct GemmCfg {
+  static constexpr int kEpiWarps = 4 * EG;
+  static constexpr int kThreads = 64 + 128 * EG;  // TMA warp + MMA warp + EG epilogue warpgroups
   static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
   static constexpr int kBBytes = (BN / CG) * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kMine = (BN / 32 + 1) / 2;  // chunks of a tile per epilogue warp
+  static constexpr int kMine = (BN / 32 + EG - 1) / EG;  // chunks of a tile per epilogue warp
   static constexpr int kSlabs = RT ? kMine : ((BN == 256) ? 1 : 2);
   static constexpr int kVecBytes = 2 * 4 * 128;  // bias[4][32] + csum[4][32] floats
   static constexpr int kWarpScratch = kSlabs * 2048 + kVecBytes;
   static constexpr int kScratchBytes = kEpiWarps * kWarpScratch;
-  static constexpr int kBarBytes = 256;   // 2 x kStages + 4 pipeline barriers, 8 residual barriers, the TMEM slot
+  static constexpr int kBarBytes = 320;   // 2 x kStages + 4 pipeline barriers, kEpiWarps residual barriers, the TMEM slot
   static constexpr int kMaxSmem = 231424;  // 227 KB - 1 KB (reserved)
   static constexpr int kFit = (kMaxSmem - 1024 /*align*/ - kBarBytes - kScratchBytes) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
@@ -113,7 +116,7 @@ struct EpiState {
 };
 
 // One output tile of the epilogue, executed by one epilogue warp (quarter = TMEM lane quarter it may access = rows
-// [32 quarter, 32 quarter + 32) of the tile, grp = epilogue warpgroup 0/1 taking the 32-column chunks c = grp, grp+2, ...).
+// [32 quarter, 32 quarter + 32) of the tile, grp = epilogue warpgroup taking the 32-column chunks c = grp, grp + EG, ...).
 // t_row = TMEM address of this warp's lanes at the accumulator's first column; tfull / tfull_phase = "accumulator
 // complete" barrier.
 //
@@ -125,19 +128,20 @@ struct EpiState {
 // are column sums of that same slab.  Before the accumulator is awaited the warp has already fetched its residual row
 // segments, the bias / csum vectors of all its chunks and its row's LayerNorm statistics, so their latency overlaps
 // the tile's main loop; TMEM loads are double-buffered.
-template <int BN, int MODE, int RT, int CG = 1>
+template <int BN, int MODE, int RT, int CG = 1, int EG = 2>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt, const int nt, const uint32_t t_row,
                                               uint8_t* scratch, const int quarter, const int grp, const int lane,
                                               uint64_t* tfull, const uint32_t tfull_phase, EpiState& st, uint64_t* res_bar,
                                               const int tile_ord = 0, const int warp_id = 0) {
-  using Cfg = GemmCfg<BN, RT, CG>;
+  using Cfg = GemmCfg<BN, RT, CG, EG>;
   static_assert(RT == 0 || MODE == SG_EPI_LINEAR, "TMA residual slabs: LINEAR epilogue only");
   const bool dbg_on = (p.dbg != nullptr) && blockIdx.x == 0 && lane == 0 && tile_ord < 8;
 #define SG_GT(slot) do { if (dbg_on) p.dbg[(warp_id * 8 + tile_ord) * 8 + (slot)] = clock64(); } while (0)
   SG_GT(0);
   const int r = quarter * 32 + lane;
   constexpr int kChunks = BN / 32;
-  constexpr int kMine = (kChunks + 1) / 2;  // chunks per warpgroup (<= 4)
+  constexpr int kMine = Cfg::kMine;  // chunks per warp (<= 4)
+  constexpr int kVB = (EG == 2) ? 2 : 1;  // TMEM-load / residual register sets (3-4 warpgroups: 112-128 registers per thread)
   const int tx = mt % p.tiles_x;
   const int ty = (mt / p.tiles_x) % p.tiles_y;
   const int tn = mt / (p.tiles_x * p.tiles_y);
@@ -165,10 +169,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
   // ---- before the accumulator is awaited: everything that comes from global memory -------------------------------
   // RT = 0: the row's residual segment of the NEXT chunk is fetched while the current one is processed (the first
   // before the accumulator is awaited); two register sets instead of one per chunk
-  [[maybe_unused]] uint4 res[2][4];
+  [[maybe_unused]] uint4 res[kVB][4];
   [[maybe_unused]] auto fetch_res = [&](const int ci, uint4 (&dst)[4]) {
-    const int col0 = nt * BN + (grp + 2 * ci) * 32;
-    if (use_res && row_ok && grp + 2 * ci < kChunks && col0 < p.N) {
+    const int col0 = nt * BN + (grp + EG * ci) * 32;
+    if (use_res && row_ok && grp + EG * ci < kChunks && col0 < p.N) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) dst[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + m * p.ldr + col0) + i);
     }
@@ -181,12 +185,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
       int nvalid = 0;
 #pragma unroll
       for (int ci = 0; ci < kMine; ++ci)
-        if (grp + 2 * ci < kChunks && nt * BN + (grp + 2 * ci) * 32 < p.N) ++nvalid;
+        if (grp + EG * ci < kChunks && nt * BN + (grp + EG * ci) * 32 < p.N) ++nvalid;
       mbar_arrive_expect_tx(res_bar, static_cast<uint32_t>(nvalid) * 2048u);
 #pragma unroll
       for (int ci = 0; ci < kMine; ++ci) {
-        const int col0 = nt * BN + (grp + 2 * ci) * 32;
-        if (grp + 2 * ci < kChunks && col0 < p.N) {
+        const int col0 = nt * BN + (grp + EG * ci) * 32;
+        if (grp + EG * ci < kChunks && col0 < p.N) {
           bulk_wait_group_read_n(kMine - 1 - ci);
           tma_load_4d(reinterpret_cast<void*>(scratch + ci * 2048), &p.res_map, res_bar, col0, slab_x, slab_y, slab_n);
         }
@@ -198,8 +202,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
   __syncwarp();
 #pragma unroll
   for (int ci = 0; ci < kMine; ++ci) {
-    const int col0 = nt * BN + (grp + 2 * ci) * 32;
-    const bool ok = (grp + 2 * ci < kChunks) && (col0 < p.N);
+    const int col0 = nt * BN + (grp + EG * ci) * 32;
+    const bool ok = (grp + EG * ci < kChunks) && (col0 < p.N);
     if (p.bias != nullptr) sts32(bias_u32 + ci * 128 + lane * 4, ok ? __float_as_uint(__ldg(p.bias + col0 + lane)) : 0u);
     if (use_ln) sts32(csum_u32 + ci * 128 + lane * 4, ok ? __float_as_uint(__ldg(p.ln_csum + col0 + lane)) : 0u);
   }
@@ -223,16 +227,24 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
   SG_GT(2);
-  uint32_t v[2][32];
-  if (grp < kChunks) tmem_ld32(t_row + grp * 32, v[0]);
+  uint32_t v[kVB][32];
+  if (kVB == 2 && grp < kChunks) tmem_ld32(t_row + grp * 32, v[0]);
 #pragma unroll
   for (int ci = 0; ci < kMine; ++ci) {
-    const int c = grp + 2 * ci;
+    const int c = grp + EG * ci;
     if (c < kChunks) {  // warp-uniform
+      if constexpr (kVB == 1) {
+        tmem_ld32(t_row + c * 32, v[0]);
+        if constexpr (MODE == SG_EPI_LINEAR && RT == 0) {
+          if (ci > 0) fetch_res(ci, res[0]);
+        }
+      }
       tmem_ld_wait();
-      if (ci + 1 < kMine && c + 2 < kChunks) {  // overlap the math below
-        tmem_ld32(t_row + (c + 2) * 32, v[(ci + 1) & 1]);
-        if constexpr (MODE == SG_EPI_LINEAR && RT == 0) fetch_res(ci + 1, res[(ci + 1) & 1]);
+      if constexpr (kVB == 2) {
+        if (ci + 1 < kMine && c + EG < kChunks) {  // overlap the math below
+          tmem_ld32(t_row + (c + EG) * 32, v[(ci + 1) & 1]);
+          if constexpr (MODE == SG_EPI_LINEAR && RT == 0) fetch_res(ci + 1, res[(ci + 1) & 1]);
+        }
       }
       const int col0 = nt * BN + c * 32;
       if (col0 < p.N) {  // warp-uniform
@@ -240,7 +252,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
         // two elements (the small-K GEMMs are bound by the epilogue's instruction count)
         float2 f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = make_float2(__uint_as_float(v[ci & 1][2 * j]), __uint_as_float(v[ci & 1][2 * j + 1]));
+        for (int j = 0; j < 16; ++j) f[j] = make_float2(__uint_as_float(v[ci % kVB][2 * j]), __uint_as_float(v[ci % kVB][2 * j + 1]));
         if (use_ln) {
           // LN(x) W^T + b' = rstd (x W'^T - mean csum) + b': acc holds x W'^T
           const float2 nm = make_float2(-ln_mean, -ln_mean), rs2 = make_float2(ln_rstd, ln_rstd);
@@ -328,7 +340,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
               } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const uint4 q = res[ci & 1][j];
+                  const uint4 q = res[ci % kVB][j];
                   w[4 * j] = hfma2_bf16(sc, q.x, w[4 * j]);
                   w[4 * j + 1] = hfma2_bf16(sc, q.y, w[4 * j + 1]);
                   w[4 * j + 2] = hfma2_bf16(sc, q.z, w[4 * j + 2]);
@@ -422,7 +434,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const int mt
   }
   if constexpr (MODE == SG_EPI_LINEAR) {
     if (row_out && row_ok)
-      reinterpret_cast<float2*>(p.row_stats_out)[static_cast<long long>(nt * 2 + grp) * p.M + m] = make_float2(rs2_acc.x + rs2_acc.y, rq2_acc.x + rq2_acc.y);
+      reinterpret_cast<float2*>(p.row_stats_out)[static_cast<long long>(nt * EG + grp) * p.M + m] = make_float2(rs2_acc.x + rs2_acc.y, rq2_acc.x + rq2_acc.y);
   }
   SG_GT(3);
 #undef SG_GT

@@ -199,6 +199,11 @@ class UNetEngine:
         # change across denoising steps, so the pipeline projects them once per prompt (project_text)
         order = [t for b in self.down if b["attn"] for t in b["attn"]] + self.mid["attn"] + \
                 [t for b in self.up if b["attn"] for t in b["attn"]]
+        # key of the last tapped feature in execution order (forward(taps_only=True) stops there)
+        self.last_tap_key = None
+        for i, b in enumerate(self.up):
+            if b["attn"]:
+                self.last_tap_key = f"up_{i}_{len(b['attn'])}"
         off = 0
         for t in order:
             t["kv2_off"] = off
@@ -277,9 +282,9 @@ class UNetEngine:
         with torch.cuda.device(self.dev):
             return ops.linear(text.view(n * L, d), self.w_kv2_all, out)
 
-    def _transformer(self, p, xa: Act, text_kv, n_text_tokens, image, kv_map, n_kv_lanes):
+    def _transformer(self, p, xa: Act, text_kv, n_text_tokens, image, kv_map, n_kv_lanes, tap_only=False):
         """xa (n, h, w, c); text_kv (n * L, n_kv2) bf16 from project_text; image None or (n_kv, R*hw, c) bf16.
-        Returns (out Act (n, h, w, c), tap (n, hw, c))."""
+        Returns (out Act (n, h, w, c), tap (n, hw, c)); tap_only: stop once the tapped feature exists -> (None, tap)."""
         n, h, w, _ = xa.t.shape
         hw, c, heads, hd = h * w, p["c"], p["heads"], p["hd"]
         m = n * hw
@@ -299,6 +304,8 @@ class UNetEngine:
         ops.attention(qkv, qkv[:, c:], qkv[:, 2 * c:], a1, n, heads, hd, hw, hw, st, st, st)
         h1, rs1 = self._new(m, c), row_stats(c, c)  # residual stream after self-attention == the tapped diffusion feature
         ops.linear(a1, p["w_o1"], h1, bias=p["b_o1"], residual=h0, row_stats_out=rs1)
+        if tap_only:
+            return None, h1.view(n, hw, c)
         # --- text (+ image) cross attention (LN2 / LN4 folded into the Q projections)
         q2 = self._new(m, c)
         ops.linear(h1, p["q2"][0], q2, bias=p["q2"][2], ln=(rs1, p["q2"][1], 1e-5))
@@ -369,13 +376,18 @@ class UNetEngine:
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, sample, timestep, encoder_hidden_states, image_hidden_states=None, kv_map=None, text_kv=None,
-                stats=None):
+                stats=None, taps_only=False):
         """text_kv: optional result of project_text(encoder_hidden_states) (cached across steps by the pipeline);
-        stats: optional caller-owned GroupNorm workspace (ops.groupnorm_ws) — a captured CUDA graph must own its own."""
+        stats: optional caller-owned GroupNorm workspace (ops.groupnorm_ws) — a captured CUDA graph must own its own;
+        taps_only: the caller only consumes the tapped features (the pipeline's feature pass, model/pipeline.py:431-436
+        keeps `[1]` of the UNet output and drops the sample): the forward stops after the last tap — the rest of the last
+        transformer block, conv_norm_out and conv_out of that pass are dead code — and returns (None, taps)."""
         with torch.cuda.device(self.dev):  # every launcher enqueues on the current device's current stream
-            return self._forward(sample, timestep, encoder_hidden_states, image_hidden_states, kv_map, text_kv, stats)
+            return self._forward(sample, timestep, encoder_hidden_states, image_hidden_states, kv_map, text_kv, stats,
+                                 taps_only)
 
-    def _forward(self, sample, timestep, encoder_hidden_states, image_hidden_states, kv_map, text_kv, stats):
+    def _forward(self, sample, timestep, encoder_hidden_states, image_hidden_states, kv_map, text_kv, stats,
+                 taps_only=False):
         dev = self.dev
         n, _, h, w = sample.shape
         if (h % (1 << self.model.num_upsamplers)) or (w % (1 << self.model.num_upsamplers)):
@@ -421,6 +433,9 @@ class UNetEngine:
                                      silu_in=True)
 
         taps: Dict[str, torch.Tensor] = {}
+        if taps_only and image_hidden_states is not None:
+            raise ValueError("taps_only is the feature pass: no image_hidden_states")
+        last_tap = self.last_tap_key if taps_only else None
 
         def attn(p, xa, hh, ww, key):
             image = None
@@ -433,7 +448,7 @@ class UNetEngine:
                                      f"(lanes, R*{hh * ww}, {p['c']})")
                 if kv_map is None and image.shape[0] != n:
                     raise ValueError(f"image_hidden_states[{key!r}] has {image.shape[0]} lanes for a batch of {n}")
-            out, tap = self._transformer(p, xa, text_kv, L, image, kv_map, 0)
+            out, tap = self._transformer(p, xa, text_kv, L, image, kv_map, 0, tap_only=(key == last_tap))
             if img is None:
                 taps[key] = tap
             return out
@@ -464,6 +479,8 @@ class UNetEngine:
                 x = self._resnet(rp, x, skips.pop(), lane_bias)
                 if blk["attn"] is not None:
                     x = attn(blk["attn"][j], x, hh, ww, f"up_{i}_{j + 1}")
+                    if x is None:  # taps_only: that was the last tap
+                        return None, taps
             if blk["up"] is not None:
                 x = self._upsample(blk["up"], x)
                 hh, ww = hh * 2, ww * 2

@@ -9,11 +9,15 @@ Restructuring relative to the reference (results unchanged; SURVEY.md §7 item 7
     (model/pipeline.py:441-443) never happens;
   * the reference's third feature-pass CFG lane duplicates the second (model/pipeline.py:429-430);
     it is not recomputed: denoise-pass lanes [image] and [text+image] share one K/V lane (kv_map);
+  * the feature pass stops at its last tapped layer: the reference keeps only `[1]` (the tapped maps) of that UNet
+    call (model/pipeline.py:433-435) and drops the sample, so the rest of the last transformer block, conv_norm_out
+    and conv_out of the feature pass are dead code (engine.forward(taps_only=True); ~1 % of a step's FLOPs);
   * a whole denoising step is captured once into a CUDA graph and replayed for the remaining steps.
 Tokenizer / CLIP / VAE are the caller's torch modules and run either side of the hot path unchanged.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Union
 
@@ -24,6 +28,8 @@ from . import ops
 from .scheduler import DDIMScheduler
 
 F32 = torch.float32
+# SG_FEATURE_TAIL=1 runs the feature pass to its (unused) end, for A/B timing
+_SKIP_FEATURE_TAIL = os.environ.get("SG_FEATURE_TAIL", "0") != "1"
 
 
 @dataclass
@@ -124,8 +130,9 @@ class _DenoiseLoop:
         nf, B = self.nf, self.B
         lat_shape = self.latents.shape[1:]
         ops.add_noise(self.f_src.view(nf, *lat_shape), self.f_eps.view(nf, *lat_shape), self.acp, self.par_i, self.f_noisy)
+        # the feature pass only yields the 16 tapped maps (model/pipeline.py:431-436 takes `[1]`): its dead tail is not run
         taps = self.eng.forward(self.f_noisy, self.par[:nf], self.f_text.view(nf, *self.f_text.shape[3:]), None,
-                                text_kv=self.f_kv, stats=self.stats)[1]
+                                text_kv=self.f_kv, stats=self.stats, taps_only=_SKIP_FEATURE_TAIL)[1]
         cond = {k: v.view(2 * B, -1, v.shape[-1]) for k, v in taps.items()}
         self.lat3.view(3, B, -1).copy_(self.latents.view(1, B, -1).expand(3, B, -1))
         eps3 = self.eng.forward(self.lat3, self.par[nf:nf + 3 * B], self.m_text.view(3 * B, *self.m_text.shape[2:]), cond,

@@ -2,6 +2,7 @@
 on identical bf16-rounded inputs.  Tolerances: bf16 output rounding (2^-8 relative) plus fp32
 accumulation-order noise; stated per test."""
 import math
+import os
 
 import pytest
 import torch
@@ -155,6 +156,35 @@ def test_attention_fused_qkv_kv_map_and_peaked_scores():
     sp2 = lambda t, L: t.float().view(t.shape[0], L, heads, d).transpose(1, 2)
     ref = F.scaled_dot_product_attention(sp2(q, 128), sp2(k[idx], 384), sp2(v[idx], 384)).transpose(1, 2).reshape(3, 128, c)
     close(out, ref, rel=0.01, abs_=0.004)
+
+
+_MC_SNIPPET = """
+import torch, torch.nn.functional as F
+from storygen_b200 import ops
+torch.manual_seed(0)
+for d, heads, n, nq, nk, scale in [(40, 8, 2, 1024, 1024, 1.0), (40, 4, 2, 300, 260, 2.5), (32, 2, 2, 512, 640, 1.0)]:
+    c = heads * d
+    q, k, v = [(torch.randn(n, L, c, device="cuda") * scale).to(torch.bfloat16) for L in (nq, nk, nk)]
+    out = torch.empty(n, nq, c, dtype=torch.bfloat16, device="cuda")
+    lse = torch.empty(n, heads, nq, dtype=torch.float32, device="cuda")
+    ops.attention(q, k, v, out, n, heads, d, nq, nk, (nq * c, c), (nk * c, c), (nk * c, c), lse=lse)
+    sp = lambda t, L: t.float().view(n, L, heads, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp(q, nq), sp(k, nk), sp(v, nk)).transpose(1, 2).reshape(n, nq, c)
+    err = (out.float() - ref).abs().max().item()
+    s = torch.einsum("nqhd,nkhd->nhqk", sp(q, nq).transpose(1, 2), sp(k, nk).transpose(1, 2)) * d ** -0.5
+    lerr = (lse - torch.logsumexp(s, -1) * 1.4426950408889634).abs().max().item()
+    assert err <= 0.02 * scale and lerr <= 0.02, (d, nq, nk, err, lerr)
+print("MC_OK")
+"""
+
+
+def test_attention_many_cta_variant_opt_in():
+    """attn_mc_kernel (four small CTAs per SM, 64-key tiles; SG_ATTN_MC=1) is kept as an opt-in variant: the switch is read
+    once per process, so it is exercised in a child process (ragged nq / nk, the lazy-rescale path, the log-sum-exp rows)."""
+    import subprocess, sys
+    env = dict(os.environ, SG_ATTN_MC="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", _MC_SNIPPET], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "MC_OK" in r.stdout, r.stdout + r.stderr
 
 
 @pytest.mark.parametrize("c0,c1,hw,groups,silu,eps", [(320, 0, 4096, 32, True, 1e-5), (1280, 640, 256, 32, True, 1e-5),

@@ -112,6 +112,30 @@ def test_text_kv_cache_is_bit_identical(tiny):
         eng.forward(sample, t, text, text_kv=kv[:-1])
 
 
+def test_feature_pass_stops_at_the_last_tap(tiny):
+    """The pipeline's feature pass keeps only the tapped maps (model/pipeline.py:433-435 takes `[1]`); with taps_only the
+    engine stops after the last of them: same 16 maps bit for bit, no sample, fewer launches."""
+    _, unet = tiny
+    eng = unet.engine()
+    g = torch.Generator("cpu").manual_seed(12)
+    n, L, D = 2, 77, unet.config.cross_attention_dim
+    sample = torch.randn(n, 4, 32, 32, generator=g).to(DEV)
+    text = torch.randn(n, L, D, generator=g).to(DEV)
+    t = torch.tensor([300.0, 20.0], device=DEV)
+    c0 = _lib.launch_count()
+    out_a, taps_a = eng.forward(sample, t, text)
+    c1 = _lib.launch_count()
+    out_b, taps_b = eng.forward(sample, t, text, taps_only=True)
+    c2 = _lib.launch_count()
+    assert out_b is None and out_a is not None
+    assert list(taps_a) == list(taps_b) and list(taps_b)[-1] == eng.last_tap_key
+    assert all(torch.equal(taps_a[k], taps_b[k]) for k in taps_a)
+    assert c2 - c1 < c1 - c0
+    with pytest.raises(ValueError):
+        eng.forward(sample, t, text, image_hidden_states={k: v for k, v in taps_a.items()}, taps_only=True)
+
+
+
 def test_full_size_sd15_unet_vs_oracle():
     ora, mod = build(SD15_CONFIG, 1)
     x, t, txt = unet_inputs(1, 768, seed=77)
