@@ -44,6 +44,10 @@ GF_DENOISE_PASS = {1: 976.9, 3: 1273.1, 5: 1569.3}
 GF_ATTN3_KV_PROJ_PER_FRAME = 25.6  # attn3 to_k/to_v over one prior frame's 16 tapped maps, per K/V lane
 GF_UPSAMPLE_CONVS = 67.95  # the 3 Upsample2D convs of one UNet call (2*256*1280*11520 + 2*1024*1280*11520 + 2*4096*640*5760)
 UPSAMPLE_EXECUTED_FRACTION = 4.0 / 9.0  # run as four 2x2-tap sub-pixel convolutions of the low-resolution tensor
+# dead tail of a feature pass (everything after the last tapped map; the reference computes it and drops it, model/pipeline.py:433-435):
+# attn2 to_q + core + to_out, GEGLU FF, proj_out of the last 64x64 transformer block, conv_out
+GF_FEATURE_TAIL = (2 * 4096 * 320 * 320 * 3 + 4 * 4096 * 77 * 320 + 2 * 4096 * 320 * 2560 + 2 * 4096 * 1280 * 320
+                   + 2 * 4096 * 2880 * 4) / 1e9
 
 
 def gf_denoise(R: int) -> float:
@@ -57,11 +61,11 @@ def tflop_per_image_reference(R: int, steps: int) -> float:
 
 def tflop_per_image_executed(R: int, steps: int) -> float:
     """What THIS path executes per image: feature passes on 2 of the 3 CFG lanes (the third duplicates the second,
-    model/pipeline.py:429-430), 3 denoise lanes of which two share one attn3 K/V projection (kv_map), and the
-    up-sampling convolutions as sub-pixel phases (4/9 of their dense FLOPs)."""
+    model/pipeline.py:429-430) and only up to their last tapped map, 3 denoise lanes of which two share one attn3 K/V
+    projection (kv_map), and the up-sampling convolutions as sub-pixel phases (4/9 of their dense FLOPs)."""
     feature_lanes, denoise_lanes, kv_lanes = 2, 3, 2
     up_saved = GF_UPSAMPLE_CONVS * (1.0 - UPSAMPLE_EXECUTED_FRACTION)  # per lane and UNet call
-    per_step = feature_lanes * R * (GF_FEATURE_PASS - up_saved) + denoise_lanes * (gf_denoise(R) - up_saved) \
+    per_step = feature_lanes * R * (GF_FEATURE_PASS - up_saved - GF_FEATURE_TAIL) + denoise_lanes * (gf_denoise(R) - up_saved) \
         - (denoise_lanes - kv_lanes) * R * GF_ATTN3_KV_PROJ_PER_FRAME
     return steps * per_step / 1e3
 
