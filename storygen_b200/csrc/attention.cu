@@ -1080,6 +1080,210 @@ __global__ void __launch_bounds__(AttnMcCfg<D>::kThreads, AttnMcCfg<D>::kCtasPer
   }
 }
 
+// =================================================================================================================
+// attn_text_kernel: the text cross-attention (77 tokens) at head dims < 64, one K/V tile of up to 80 keys.
+// A CTA is a pure latency chain (TMA -> Q K^T -> softmax -> P V -> store, ~4 us) with almost no work, so what counts is how
+// many chains an SM holds: S (80 columns, P written over it in place) + O (d + ones column -> 48 columns) = 128 TMEM columns,
+// 36 KB of shared memory, 6 warps -- four CTAs per SM instead of the two of attn_kernel<D, 1, SHORT>.  The softmax makes two
+// passes over S in TMEM (row max, then exp / pack in 16-column chunks), so a thread never holds more than one chunk.
+//   warp 0: TMA (Q, K, V) + the ones column of V      warp 1: tcgen05 issuer      warps 2-5: softmax, thread = query row
+// =================================================================================================================
+template <int D>
+struct AttnTextCfg {
+  static_assert(D < 64 && D % 8 == 0, "one 64-channel atom with room for the ones column");
+  static constexpr int KQ = (D + 15) / 16;
+  static constexpr int kNPV = (D + 16) & ~15;
+  static constexpr int kOnesChunk = D / 8;
+  static constexpr int kTK = 80;                      // keys per tile (5 UMMA k-steps of P V; Q K^T with N = 80)
+  static constexpr int kQBytes = 128 * 128;
+  static constexpr int kKvBytes = kTK * 128;
+  static constexpr int kThreads = 192;
+  static constexpr int kCtasPerSm = 4;
+  static constexpr int kColO = kTK;
+  static constexpr int kTmemCols = 128;
+  static constexpr int kSmemBytes = kQBytes + 2 * kKvBytes + 1024 + 128;
+  static_assert(kColO + kNPV <= kTmemCols, "S + O must fit 128 TMEM columns");
+};
+
+template <int D>
+__global__ void __launch_bounds__(AttnTextCfg<D>::kThreads, AttnTextCfg<D>::kCtasPerSm)
+    attn_text_kernel(const __grid_constant__ AttnKParams p) {
+  using Cfg = AttnTextCfg<D>;
+  constexpr int TK = Cfg::kTK;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* q_smem = smem;
+  uint8_t* k_smem = smem + Cfg::kQBytes;
+  uint8_t* v_smem = k_smem + Cfg::kKvBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + Cfg::kKvBytes);
+  uint64_t* q_full = bars;       // TMA -> softmax warps
+  uint64_t* k_full = bars + 1;   // TMA -> MMA
+  uint64_t* v_full = bars + 2;   // TMA -> ones column
+  uint64_t* v_ready = bars + 3;  // ones column -> MMA
+  uint64_t* q_ready = bars + 4;  // softmax warps -> MMA (Q pad zeroed)
+  uint64_t* s_full = bars + 5;   // MMA -> softmax
+  uint64_t* p_full = bars + 6;   // softmax -> MMA
+  uint64_t* o_done = bars + 7;   // MMA -> softmax
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(k_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_ready, 1);
+    mbar_init(q_ready, 4);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    // ===================== TMA loader, then the ones column of V =====================
+    const int kv_img = (p.kv_map != nullptr) ? p.kv_map[img] : img;
+    mbar_arrive_expect_tx_w(q_full, Cfg::kQBytes);
+    tma_load_3d_w(q_smem, &p.q_map, q_full, head * D, q0, img);
+    mbar_arrive_expect_tx_w(k_full, Cfg::kKvBytes);
+    tma_load_3d_w(k_smem, &p.k_map, k_full, head * D, 0, kv_img);
+    mbar_arrive_expect_tx_w(v_full, Cfg::kKvBytes);
+    tma_load_3d_w(v_smem, &p.v_map, v_full, head * D, 0, kv_img);
+    mbar_wait(v_full, 0);
+    const uint4 ones = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);  // 8 x bf16 1.0
+    const uint32_t tile = smem_u32(v_smem);
+#pragma unroll
+    for (int rr = 0; rr < (TK + 31) / 32; ++rr) {
+      const int row = rr * 32 + lane;
+      if (row < TK) sts128(tile + row * 128 + ((Cfg::kOnesChunk ^ (row & 7)) << 4), ones);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(v_ready);
+  } else if (warp == 1) {
+    // ===================== tcgen05 issuer =====================
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, TK, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, Cfg::kNPV, 0, 1);  // B (= V) is MN-major
+    const uint32_t q_addr = smem_u32(q_smem), k_addr = smem_u32(k_smem), v_addr = smem_u32(v_smem);
+    mbar_wait(q_ready, 0);
+    mbar_wait(k_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int ks = 0; ks < Cfg::KQ; ++ks)
+      umma_ss_w(tmem_base, make_smem_desc(q_addr + ks * 32, 16, 1024, kLayoutSW128),
+                make_smem_desc(k_addr + ks * 32, 16, 1024, kLayoutSW128), idesc_qk, ks != 0);
+    umma_commit_w(s_full);
+    mbar_wait(v_ready, 0);
+    mbar_wait(p_full, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int ks = 0; ks < TK / 16; ++ks)
+      umma_ts_w(tmem_base + Cfg::kColO, tmem_base + ks * 8, make_smem_desc(v_addr + ks * 2048, kAtomBytes, 1024, kLayoutSW128),
+                idesc_pv, ks != 0);
+    umma_commit_w(o_done);
+  } else {
+    // ===================== softmax: thread = query row =====================
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_base;
+    const uint32_t o_tmem = tmem_base + lane_base + Cfg::kColO;
+
+    mbar_wait(q_full, 0);
+    if constexpr (D % 16 != 0) {
+      uint4* dst = reinterpret_cast<uint4*>(q_smem + r * 128 + (((D / 8) ^ (r & 7)) << 4));
+      *dst = make_uint4(0, 0, 0, 0);
+      fence_proxy_async_smem();
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(q_ready);
+
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    // pass 1: row max over the valid keys
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int c = 0; c < TK / 16; ++c) {
+      uint32_t sv[16];
+      tmem_ld16(s_tmem + c * 16, sv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c * 16 + i < p.nk) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(sv[i]));
+    }
+    const float m_used = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), nm2 = make_float2(-m_used, -m_used);
+    // pass 2: P = 2^(scale * S - max) as bf16 over S, chunk by chunk (P columns [8c, 8c + 8) lie below the S columns still unread)
+#pragma unroll
+    for (int c = 0; c < TK / 16; ++c) {
+      uint32_t sv[16], pk[8];
+      tmem_ld16(s_tmem + c * 16, sv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        const float2 x = ffma2(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sc2, nm2);
+        const float e0 = (c * 16 + i < p.nk) ? fast_exp2(x.x) : 0.f;
+        const float e1 = (c * 16 + i + 1 < p.nk) ? fast_exp2(x.y) : 0.f;
+        pk[i >> 1] = pack_bf16x2(e0, e1);
+      }
+      tmem_st8(s_tmem + c * 8, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p_full);
+
+    // O / l -> global (only the d valid channels of this head)
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    const int q = q0 + r;
+    bf16* orow = p.o + static_cast<long long>(img) * p.o_stride_n + static_cast<long long>(q) * p.o_stride_t + head * D;
+    float inv_l = 0.f;
+#pragma unroll
+    for (int c = Cfg::kNPV / 16 - 1; c >= 0; --c) {  // the chunk with column D (the row sum) first
+      uint32_t ov[16];
+      tmem_ld16(o_tmem + c * 16, ov);
+      tmem_ld_wait();
+      if (c == D / 16) {
+        const float l_run = __uint_as_float(ov[D % 16]);
+        inv_l = 1.0f / l_run;
+        if (p.lse != nullptr && q < p.nq)
+          p.lse[(static_cast<long long>(img) * p.n_heads + head) * p.nq + q] = m_used + log2f(l_run);
+      }
+      if (q < p.nq) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (c * 16 + g * 8 < D) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(ov[8 * g + 0]) * inv_l, __uint_as_float(ov[8 * g + 1]) * inv_l);
+            w.y = pack_bf16x2(__uint_as_float(ov[8 * g + 2]) * inv_l, __uint_as_float(ov[8 * g + 3]) * inv_l);
+            w.z = pack_bf16x2(__uint_as_float(ov[8 * g + 4]) * inv_l, __uint_as_float(ov[8 * g + 5]) * inv_l);
+            w.w = pack_bf16x2(__uint_as_float(ov[8 * g + 6]) * inv_l, __uint_as_float(ov[8 * g + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c * 16 + g * 8) = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 template <int D, int QT, bool DBG = false, bool SHORT = false>
 static int launch_attn(const AttnKParams& kp, int nq, int heads, int lanes, cudaStream_t stream) {
   using Cfg = AttnCfg<D, QT, SHORT>;
@@ -1120,10 +1324,31 @@ static bool use_attn_mc(int head_dim, int nk) {
   return enabled && (head_dim == 40 || head_dim == 32) && nk > 128;
 }
 
+template <int D>
+static int launch_attn_text(const AttnKParams& kp, int nq, int heads, int lanes, cudaStream_t stream) {
+  using Cfg = AttnTextCfg<D>;
+  static std::atomic<uint64_t> configured{0};
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(attn_text_kernel<D>), Cfg::kSmemBytes, &configured)) return rc;
+  dim3 grid((nq + 127) / 128, heads, lanes);
+  attn_text_kernel<D><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
+  count_launch();
+  return static_cast<int>(cudaGetLastError());
+}
+
+// head dims 40 / 32 with at most 80 keys (the 77-token text cross-attention): attn_text_kernel.  SG_ATTN_TEXT=0 disables (A/B runs).
+static bool use_attn_text(int head_dim, int nk) {
+  static const bool enabled = [] {
+    const char* e = getenv("SG_ATTN_TEXT");
+    return e == nullptr || e[0] != '0';
+  }();
+  return enabled && (head_dim == 40 || head_dim == 32) && nk <= 80;
+}
+
 // two query tiles per CTA whenever there are at least two (and the head dim leaves TMEM room)
 template <int D>
 static int launch_attn_auto(const AttnKParams& kp, int nq, int heads, int lanes, cudaStream_t stream) {
   if constexpr (D < 64) {
+    if (use_attn_text(D, kp.nk)) return launch_attn_text<D>(kp, nq, heads, lanes, stream);
     if (use_attn_mc(D, kp.nk)) return launch_attn_mc<D>(kp, nq, heads, lanes, stream);
   }
   if constexpr (D <= 128) {
@@ -1160,7 +1385,8 @@ extern "C" int sg_attention(const sg_attn_args* a, void* stream_v) {
   memset(&kp, 0, sizeof(kp));
   int rc;
   if ((rc = make_tok_map(&kp.q_map, a->q, C, a->nq, a->n_lanes, a->q_stride_t, a->q_stride_n)) != 0) return rc;
-  const uint32_t kv_box = use_attn_mc(a->head_dim, a->nk) ? 64 : 128;  // keys per K / V tile of the kernel that will run
+  // keys per K / V tile of the kernel that will run
+  const uint32_t kv_box = use_attn_text(a->head_dim, a->nk) ? 80 : (use_attn_mc(a->head_dim, a->nk) ? 64 : 128);
   if ((rc = make_tok_map(&kp.k_map, a->k, C, a->nk, kv_lanes, a->k_stride_t, a->k_stride_n, kv_box)) != 0) return rc;
   if ((rc = make_tok_map(&kp.v_map, a->v, C, a->nk, kv_lanes, a->v_stride_t, a->v_stride_n, kv_box)) != 0) return rc;
   kp.o = static_cast<bf16*>(a->o);

@@ -126,7 +126,8 @@ def test_conv3x3_stride2():
 
 
 @pytest.mark.parametrize("d,heads,n,nq,nk", [(40, 8, 2, 4096, 4096), (40, 8, 3, 1024, 77), (80, 8, 2, 1024, 3072), (160, 8, 2, 256, 768),
-                                             (160, 8, 3, 64, 192), (32, 2, 2, 512, 640), (64, 2, 1, 256, 256), (128, 2, 2, 64, 64)])
+                                             (160, 8, 3, 64, 192), (32, 2, 2, 512, 640), (64, 2, 1, 256, 256), (128, 2, 2, 64, 64),
+                                             (32, 2, 2, 200, 80), (40, 4, 1, 130, 33), (40, 2, 2, 128, 1)])
 def test_attention(d, heads, n, nq, nk):
     c = heads * d
     q, k, v = rnd(n, nq, c, seed=1), rnd(n, nk, c, seed=2), rnd(n, nk, c, seed=3)
@@ -155,6 +156,21 @@ def test_attention_fused_qkv_kv_map_and_peaked_scores():
     idx = kv_map.long()
     sp2 = lambda t, L: t.float().view(t.shape[0], L, heads, d).transpose(1, 2)
     ref = F.scaled_dot_product_attention(sp2(q, 128), sp2(k[idx], 384), sp2(v[idx], 384)).transpose(1, 2).reshape(3, 128, c)
+    close(out, ref, rel=0.01, abs_=0.004)
+
+
+def test_attention_text_tile_log_sum_exp_rows():
+    """attn_text_kernel (Nk <= 80, head dim 40): the optional log2-domain log-sum-exp rows the backward pass consumes."""
+    d, heads, n, nq, nk = 40, 4, 2, 300, 77
+    c = heads * d
+    q, k, v = rnd(n, nq, c, seed=21), rnd(n, nk, c, seed=22), rnd(n, nk, c, seed=23)
+    out = torch.empty(n, nq, c, dtype=BF16, device=DEV)
+    lse = torch.empty(n, heads, nq, dtype=torch.float32, device=DEV)
+    ops.attention(q, k, v, out, n, heads, d, nq, nk, (nq * c, c), (nk * c, c), (nk * c, c), lse=lse)
+    sp = lambda t, L: t.float().view(n, L, heads, d).transpose(1, 2)
+    s = sp(q, nq) @ sp(k, nk).transpose(-1, -2) * d ** -0.5
+    assert (lse - torch.logsumexp(s, -1) * math.log2(math.e)).abs().max().item() <= 0.02
+    ref = (torch.softmax(s, -1) @ sp(v, nk)).transpose(1, 2).reshape(n, nq, c)
     close(out, ref, rel=0.01, abs_=0.004)
 
 
