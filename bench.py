@@ -497,9 +497,10 @@ def run_ours(args, rank, local_rank, world):
                                           "frac_of_burst": model_tf / peaks["tf_burst"],
                                           "tflop_per_image_reference_equivalent": tf_ref,
                                           "work_removed_speedup": tf_ref / tf_exec,
-                                          "note": "executed = 2R feature lanes + 3 denoise lanes - 1 shared attn3 K/V projection "
-                                                  "per image-step, up-sampling convs at 4/9 (sub-pixel phases); the reference "
-                                                  "executes 3R + 3 lanes"},
+                                          "note": "executed = 2R feature lanes (each up to its last tapped map; the reference drops the rest "
+                                                  "of that call's output) + 3 denoise lanes - 1 shared attn3 K/V projection per "
+                                                  "image-step, up-sampling convs at 4/9 (sub-pixel phases); the reference executes "
+                                                  "3R + 3 full lanes"},
                                 "ms_per_denoising_step_graph": ms_denoising_step, "eager_unet": eager},
             "cpu_baseline": cpu,
             "parity": parity,
