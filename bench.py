@@ -543,13 +543,18 @@ def run_train(args, rank, local_rank, world):
     """BASELINE cfg3: one stage-2 training step (train_StorySalon_stage2.py:258-332) at 512 px, R prior frames, batch b, bf16
     autocast: R feature passes (inference engine: no trainable parameter on that path), the denoise pass in train() mode
     (attn3 core forward + backward on the tcgen05 kernels, frozen layers as torch ops for their dgrad), masked-MSE loss,
-    backward, AdamW step on the 64 attn3 matrices.  Single GPU (DDP all-reduce of the 198 MB of attn3 gradients not wired)."""
+    backward, AdamW step on the 64 attn3 matrices.  N > 1: data parallel, batch b per rank, the 198 MB of attn3 gradients
+    averaged with one flat all-reduce per step (storygen_b200.distributed.allreduce_gradients); time = max over ranks."""
     import torch
+    import torch.distributed as dist
     import torch.nn.functional as F
 
+    from storygen_b200.distributed import allreduce_gradients, shard_range
     from storygen_b200.synthetic import synthetic_inputs, to_device
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     unet = build_model(torch, dev)
     unet.requires_grad_(False)
     trainable = []
@@ -561,10 +566,11 @@ def run_train(args, rank, local_rank, world):
     opt = torch.optim.AdamW(trainable, lr=1e-5, fused=True)
     unet.train()
     b, R = args.batch, args.frames
-    inp = to_device(synthetic_inputs(b, R, latent_hw=args.latent), dev)
+    inp = to_device(synthetic_inputs(b, R, latent_hw=args.latent, first_image=shard_range(world * b, rank, world)[0]), dev)
     from storygen_b200.scheduler import DDIMScheduler
     acp = DDIMScheduler().alphas_cumprod.to(dev)
-    g = torch.Generator(device=dev).manual_seed(0)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    grad_bytes = 0
 
     def step():
         t = torch.randint(0, 1000, (b,), device=dev, generator=g)
@@ -582,21 +588,33 @@ def run_train(args, rank, local_rank, world):
         pred = unet(noisy, t, inp["text_cond"], image_hidden_states=cond, return_dict=False)[0]
         loss = F.mse_loss(pred.float(), noise)
         loss.backward()
+        nonlocal grad_bytes
+        grad_bytes = allreduce_gradients(trainable)
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
 
     for _ in range(max(1, args.warmup)):
         step()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         loss = step()
     e1.record()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    print(json.dumps({"metric": "train_images_per_sec_512px_stage2", "value": b / (ms * 1e-3), "unit": "images/s", "n_gpus": 1,
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank != 0:
+        return
+    print(json.dumps({"metric": "train_images_per_sec_512px_stage2", "value": world * b / (ms * 1e-3), "unit": "images/s",
+                      "n_gpus": world, "scaling": "weak", "grad_allreduce_bytes_per_step": grad_bytes,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "bf16",
                       "data": "synthetic", "loss": float(loss.item()),
                       "config": {"workload": f"StoryGen stage-2 training step (BASELINE cfg3): SD-1.5 UNet+attn3, 512px, {R} prior "

@@ -4,7 +4,7 @@ per GPU with NO data-path collective, and the final latents are collected with a
 (NCCL over NVLink on GPUs; gloo in the CPU tests)."""
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Iterable, Tuple
 
 import torch
 import torch.distributed as dist
@@ -37,3 +37,24 @@ def gather_latents(local: torch.Tensor, global_batch: int, group=None) -> torch.
     if all(c == mx for c in counts):
         return out
     return torch.cat([out[r * mx: r * mx + counts[r]] for r in range(world)], dim=0)
+
+
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None) -> int:
+    """Data-parallel stage-2 training (train_StorySalon_stage2.py:168-177, 327 under accelerate's DDP): average the
+    gradients of the trainable (attn3) parameters over the ranks with ONE all-reduce of a flat fp32 bucket, in place.
+    The 80 attn3 tensors are 198 MB of fp32 gradients: ~0.5 ms over NVLink / NVSwitch against a ~145 ms step, so a single
+    bucket after backward is enough (nothing to overlap).  Returns the number of bytes reduced (0 on a single rank)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(dist.get_world_size(group))
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat.numel() * 4

@@ -1,5 +1,6 @@
 """CPU, world_size 2, gloo: the N>1 path of the benchmark — shard the global image batch by image index,
-run the (here: stand-in) per-image computation, all-gather the latents in image order."""
+run the (here: stand-in) per-image computation, all-gather the latents in image order; and the data-parallel training
+step's gradient averaging."""
 import os
 import socket
 
@@ -7,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from storygen_b200.distributed import gather_latents, shard_range
+from storygen_b200.distributed import allreduce_gradients, gather_latents, shard_range
 from storygen_b200.synthetic import synthetic_inputs
 
 
@@ -40,7 +41,14 @@ def _worker(rank, world, port, global_batch, q):
     inp = synthetic_inputs(count, 1, latent_hw=8, text_dim=16, first_image=first) if count else None
     local = (inp["latents"] * 2 + inp["noise"]) if count else torch.zeros(0, 4, 8, 8)  # stand-in for the denoise loop
     full = gather_latents(local, global_batch)
-    q.put((rank, full))
+    # data-parallel training: gradients of the trainable tensors averaged over the ranks in one flat all-reduce
+    params = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2))]
+    params[0].grad = torch.full((3, 5), float(rank + 1))
+    params[1].grad = torch.arange(7, dtype=torch.float32) * (rank + 1)
+    nbytes = allreduce_gradients(params)  # params[2] has no gradient: skipped on every rank
+    ok = (nbytes == 22 * 4 and torch.equal(params[0].grad, torch.full((3, 5), 1.5))
+          and torch.equal(params[1].grad, torch.arange(7, dtype=torch.float32) * 1.5) and params[2].grad is None)
+    q.put((rank, (full, ok)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -76,7 +84,8 @@ def _run(global_batch):
     ref = synthetic_inputs(global_batch, 1, latent_hw=8, text_dim=16)
     expect = ref["latents"] * 2 + ref["noise"]
     for r in range(2):
-        assert torch.equal(res[r], expect), f"rank {r}"
+        assert torch.equal(res[r][0], expect), f"rank {r}"
+        assert res[r][1], f"rank {r}: gradient all-reduce"
 
 
 def test_two_rank_gather_equal_shards():
