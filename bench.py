@@ -611,6 +611,8 @@ def run_train(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    if world > 1:
+        dist.destroy_process_group()
     if rank != 0:
         return
     print(json.dumps({"metric": "train_images_per_sec_512px_stage2", "value": world * b / (ms * 1e-3), "unit": "images/s",
