@@ -22,6 +22,7 @@ per Transformer2DModel (feature pass 12, denoise pass 15 kernels; + one text K/V
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -31,6 +32,8 @@ from ._lib import SG_EPI_GEGLU, SG_EPI_NCHW_F32
 from .ops import BF16, Src, taps3x3
 
 F32 = torch.float32
+# SG_FUSE_Q23=0: separate to_q GEMMs for attn2 and attn3 in the denoise pass (A/B timing)
+_FUSE_Q23 = os.environ.get("SG_FUSE_Q23", "1") != "0"
 
 
 class Act:
@@ -146,6 +149,9 @@ class UNetEngine:
         d["w_kv2"] = torch.cat([a2.to_k.weight.detach(), a2.to_v.weight.detach()], 0)  # fused across layers in _pack
         d["w_o2"], d["b_o2"] = self._bf(a2.to_out[0].weight), self._f32(a2.to_out[0].bias)
         d["q3"] = self._fold_ln(a3.to_q.weight, None, blk.norm4)
+        # denoise pass: to_q of attn2 and attn3 read the same rows (LN2 / LN4 of the same residual stream share their
+        # statistics): ONE GEMM over N = [q2 | q3]
+        d["q23"] = tuple(torch.cat([d["q2"][i], d["q3"][i]], 0).contiguous() for i in range(3))
         d["w_kv3"] = self._bf(torch.cat([a3.to_k.weight, a3.to_v.weight], 0))
         d["w_o23"] = self._bf(torch.cat([a2.to_out[0].weight, a3.to_out[0].weight], 1))
         d["b_o23"] = self._f32(a2.to_out[0].bias.detach() + a3.to_out[0].bias.detach())
@@ -306,23 +312,29 @@ class UNetEngine:
         ops.linear(a1, p["w_o1"], h1, bias=p["b_o1"], residual=h0, row_stats_out=rs1)
         if tap_only:
             return None, h1.view(n, hw, c)
-        # --- text (+ image) cross attention (LN2 / LN4 folded into the Q projections)
-        q2 = self._new(m, c)
-        ops.linear(h1, p["q2"][0], q2, bias=p["q2"][2], ln=(rs1, p["q2"][1], 1e-5))
+        # --- text (+ image) cross attention (LN2 / LN4 folded into the Q projections; one GEMM for both when attn3 runs)
+        if image is not None and _FUSE_Q23:
+            q23 = self._new(m, 2 * c)
+            ops.linear(h1, p["q23"][0], q23, bias=p["q23"][2], ln=(rs1, p["q23"][1], 1e-5))
+            q2, q3, ldq = q23, q23[:, c:], 2 * c
+        else:
+            q2, ldq = self._new(m, c), c
+            ops.linear(h1, p["q2"][0], q2, bias=p["q2"][2], ln=(rs1, p["q2"][1], 1e-5))
+            if image is not None:
+                q3 = self._new(m, c)
+                ops.linear(h1, p["q3"][0], q3, bias=p["q3"][2], ln=(rs1, p["q3"][1], 1e-5))
         L = n_text_tokens
         ld = text_kv.shape[1]
         kv2 = text_kv[:, p["kv2_off"]:]
         a2 = self._new(m, c)
-        ops.attention(q2, kv2, kv2[:, c:], a2, n, heads, hd, hw, L, (hw * c, c), (L * ld, ld), (L * ld, ld))
+        ops.attention(q2, kv2, kv2[:, c:], a2, n, heads, hd, hw, L, (hw * ldq, ldq), (L * ld, ld), (L * ld, ld))
         h2, rs2 = self._new(m, c), row_stats(c, 2 * c if image is not None else c)
         if image is not None:
-            q3 = self._new(m, c)
-            ops.linear(h1, p["q3"][0], q3, bias=p["q3"][2], ln=(rs1, p["q3"][1], 1e-5))
             nkv, nk = image.shape[0], image.shape[1]
             kv3 = self._new(nkv * nk, 2 * c)
             ops.linear(image.view(nkv * nk, c), p["w_kv3"], kv3)
             a3 = self._new(m, c)
-            ops.attention(q3, kv3, kv3[:, c:], a3, n, heads, hd, hw, nk, (hw * c, c), (nk * 2 * c, 2 * c),
+            ops.attention(q3, kv3, kv3[:, c:], a3, n, heads, hd, hw, nk, (hw * ldq, ldq), (nk * 2 * c, 2 * c),
                           (nk * 2 * c, 2 * c), n_kv_lanes=nkv, kv_map=kv_map)
             # h_t + h_i = 2h + a_t + a_i  (model/attention.py:277,291,293): one GEMM over K = [a2 | a3]
             ops.gemm([Src.rows(a2), Src.rows(a3)], [(0, 0, 0, 0, c // 64), (1, 0, 0, 0, c // 64)], (m, 1, 1),
