@@ -107,14 +107,23 @@ class _DenoiseLoop:
     def load(self, latents, text_uncond, text_cond, prev_uncond, prev_cond, frame_latents, zero_latents, noise):
         """Copy one batch of inputs (host or device tensors) into the static buffers."""
         nb = dict(non_blocking=True)
+        dev = self.latents.device
+
+        def on_dev(t):
+            # a host -> device copy_ that also changes the dtype converts on the CPU first (and then copies from pageable
+            # memory, synchronously): move the bytes as they are (asynchronous from pinned memory), cast on the device
+            return t if t.device == dev else t.to(dev, non_blocking=True)
+
         self.latents.copy_(latents, **nb)
+        zero_latents, noise = on_dev(zero_latents), on_dev(noise)
+        text_uncond, text_cond = on_dev(text_uncond), on_dev(text_cond)
         for r in range(self.R):
             self.f_src[0, :, r].copy_(zero_latents, **nb)
             self.f_src[1, :, r].copy_(frame_latents[r], **nb)
             self.f_eps[0, :, r].copy_(noise, **nb)
             self.f_eps[1, :, r].copy_(noise, **nb)
-            self.f_text[0, :, r].copy_(prev_uncond[r], **nb)
-            self.f_text[1, :, r].copy_(prev_cond[r], **nb)
+            self.f_text[0, :, r].copy_(on_dev(prev_uncond[r]), **nb)
+            self.f_text[1, :, r].copy_(on_dev(prev_cond[r]), **nb)
         self.m_text[0].copy_(text_uncond, **nb)
         self.m_text[1].copy_(text_uncond, **nb)
         self.m_text[2].copy_(text_cond, **nb)
